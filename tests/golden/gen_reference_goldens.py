@@ -1,0 +1,243 @@
+"""Generate golden vectors by RUNNING THE REFERENCE'S OWN SOURCE (read from /root/reference at generation time, never
+copied) with its absent third-party dependencies stubbed.  Run in the build container only:
+
+    python tests/golden/gen_reference_goldens.py        ->  tests/golden/ref_processors.pt, ref_embeddings.pt, ref_camera.pt
+
+What is real and what is stubbed
+  real   : animatediff/models/attention_processor.py (all processors + SoftmaxAlphaBlender), animatediff/models/embeddings.py,
+           pipeline.py::get_camera/generate_c2w/normalize_camera (exec'd from the file's AST, the module itself cannot
+           be imported because diffusers is missing)
+  stubbed: `diffusers` (Attention container with to_q/to_k/to_v/to_out, head_to_batch_dim, batch_to_head_dim,
+           get_attention_scores per diffusers 0.28.0; AlphaBlender; SinusoidalPositionalEmbedding; LabelEmbedding) and
+           `xformers.ops.memory_efficient_attention` (softmax(q k^T scale) v in fp32 -- xformers 0.0.16 is CUDA-only).
+The GPU box has no /root/reference; only the emitted .pt fixtures travel.
+"""
+import ast
+import math
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+# --------------------------------------------------------------------------------------------- stubs
+class Attention(nn.Module):
+    """diffusers 0.28.0 models/attention_processor.py::Attention, the subset the reference processors touch."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=8):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)
+        self.to_v = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim, bias=True), nn.Dropout(0.0)])
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = None
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+
+    def prepare_attention_mask(self, attention_mask, target_length, batch_size, out_dim=3):
+        assert attention_mask is None
+        return None
+
+    def head_to_batch_dim(self, tensor, out_dim=3):
+        head_size = self.heads
+        if tensor.ndim == 3:
+            batch_size, seq_len, dim = tensor.shape
+            extra_dim = 1
+        else:
+            batch_size, extra_dim, seq_len, dim = tensor.shape
+        tensor = tensor.reshape(batch_size, seq_len * extra_dim, head_size, dim // head_size)
+        tensor = tensor.permute(0, 2, 1, 3)
+        if out_dim == 3:
+            tensor = tensor.reshape(batch_size * head_size, seq_len * extra_dim, dim // head_size)
+        return tensor
+
+    def batch_to_head_dim(self, tensor):
+        head_size = self.heads
+        batch_size, seq_len, dim = tensor.shape
+        tensor = tensor.reshape(batch_size // head_size, head_size, seq_len, dim)
+        return tensor.permute(0, 2, 1, 3).reshape(batch_size // head_size, seq_len, dim * head_size)
+
+    def get_attention_scores(self, query, key, attention_mask=None):
+        assert attention_mask is None
+        baddbmm_input = torch.empty(query.shape[0], query.shape[1], key.shape[1], dtype=query.dtype)
+        scores = torch.baddbmm(baddbmm_input, query, key.transpose(-1, -2), beta=0, alpha=self.scale)
+        return scores.softmax(dim=-1).to(query.dtype)
+
+
+class AlphaBlender(nn.Module):
+    """diffusers 0.28.0 models/resnet.py::AlphaBlender, merge_strategy='learned' (2-D/3-D input path)."""
+
+    def __init__(self, alpha, merge_strategy="learned", switch_spatial_to_temporal_mix=False):
+        super().__init__()
+        assert merge_strategy == "learned"
+        self.register_parameter("mix_factor", nn.Parameter(torch.Tensor([alpha])))
+
+    def forward(self, x_spatial, x_temporal, image_only_indicator=None):
+        alpha = torch.sigmoid(self.mix_factor).to(x_spatial.dtype)
+        return alpha * x_spatial + (1.0 - alpha) * x_temporal
+
+
+class SinusoidalPositionalEmbedding(nn.Module):
+    """diffusers 0.28.0 models/embeddings.py::SinusoidalPositionalEmbedding."""
+
+    def __init__(self, embed_dim, max_seq_length=32):
+        super().__init__()
+        position = torch.arange(max_seq_length).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, embed_dim, 2) * (-math.log(10000.0) / embed_dim))
+        pe = torch.zeros(1, max_seq_length, embed_dim)
+        pe[0, :, 0::2] = torch.sin(position * div_term)
+        pe[0, :, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe)
+
+    def forward(self, x):
+        _, seq_length, _ = x.shape
+        return x + self.pe[:, :seq_length]
+
+
+class LabelEmbedding(nn.Module):
+    def __init__(self, num_classes, hidden_size, dropout_prob):
+        super().__init__()
+        self.embedding_table = nn.Embedding(num_classes + (dropout_prob > 0), hidden_size)
+
+    def forward(self, labels):
+        return self.embedding_table(labels)
+
+
+def memory_efficient_attention(query, key, value, attn_bias=None, op=None, scale=None, p=0.0):
+    """xformers.ops.memory_efficient_attention on 3-D [B*H, L, d] inputs."""
+    assert attn_bias is None
+    scale = scale if scale is not None else query.shape[-1] ** -0.5
+    s = torch.bmm(query.float(), key.float().transpose(1, 2)) * scale
+    return torch.bmm(s.softmax(-1), value.float()).to(query.dtype)
+
+
+def install_stubs():
+    def mod(name):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+    d = mod("diffusers"); du = mod("diffusers.utils"); dm = mod("diffusers.models")
+    dap = mod("diffusers.models.attention_processor"); de = mod("diffusers.models.embeddings")
+    dr = mod("diffusers.models.resnet")
+    du.USE_PEFT_BACKEND = False
+    dap.Attention = Attention
+    de.LabelEmbedding = LabelEmbedding
+    de.SinusoidalPositionalEmbedding = SinusoidalPositionalEmbedding
+    dr.AlphaBlender = AlphaBlender
+    d.utils = du; d.models = dm; dm.attention_processor = dap; dm.embeddings = de; dm.resnet = dr
+    x = mod("xformers"); xo = mod("xformers.ops")
+    xo.memory_efficient_attention = memory_efficient_attention
+    x.ops = xo
+
+
+def load_camera_fns():
+    """exec the three camera helpers out of pipeline.py without importing the module (it needs diffusers)."""
+    src = open(os.path.join(REF, "animatediff/pipelines/pipeline.py")).read()
+    tree = ast.parse(src)
+    want = {"get_camera", "generate_c2w", "normalize_camera"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    import numpy as np
+    ns = {"np": np, "torch": torch, "F": F, "math": math}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "pipeline_camera", "exec"), ns)
+    return ns["get_camera"]
+
+
+def attn_weights(attn, prefix):
+    return {f"{prefix}.to_q.weight": attn.to_q.weight.detach().clone(),
+            f"{prefix}.to_k.weight": attn.to_k.weight.detach().clone(),
+            f"{prefix}.to_v.weight": attn.to_v.weight.detach().clone(),
+            f"{prefix}.to_out.0.weight": attn.to_out[0].weight.detach().clone(),
+            f"{prefix}.to_out.0.bias": attn.to_out[0].bias.detach().clone()}
+
+
+def main():
+    install_stubs()
+    sys.path.insert(0, REF)
+    from animatediff.models import attention_processor as ap  # the reference's own file
+    from animatediff.models.embeddings import SinePositionalEncoding2D
+
+    torch.manual_seed(1234)
+    cases = []
+    for (c, heads, nv, nf, fs, b) in [(64, 8, 2, 3, 4, 1), (80, 8, 4, 4, 2, 2), (96, 8, 1, 4, 4, 1)]:
+        l = fs * fs
+        dh = c // heads
+        cd = 48
+        # ---- MVDreamI2V (attn1 of the spatial transformers)
+        attn = Attention(c, None, heads, dh)
+        proc = ap.MVDreamI2VXFormersAttnProcessor(hidden_size=c, num_views=nv, num_frames=nf)
+        nn.init.normal_(proc.to_out_i2v.weight, std=0.1); nn.init.normal_(proc.to_out_i2v.bias, std=0.1)
+        x = torch.randn(b * nv * nf, l, c)
+        with torch.no_grad():
+            y = proc(attn, x)
+        w = attn_weights(attn, "a.attn1")
+        w["a.attn1.processor.to_q_i2v.weight"] = proc.to_q_i2v.weight.detach().clone()
+        w["a.attn1.processor.to_out_i2v.weight"] = proc.to_out_i2v.weight.detach().clone()
+        w["a.attn1.processor.to_out_i2v.bias"] = proc.to_out_i2v.bias.detach().clone()
+        cases.append(dict(kind="mv_i2v", c=c, heads=heads, nv=nv, nf=nf, fs=fs, b=b, x=x, y=y, w=w))
+        # ---- plain MVDream (same regroup, no I2V branch)
+        proc0 = ap.MVDreamXFormersAttnProcessor(num_views=nv, num_frames=nf)
+        with torch.no_grad():
+            y0 = proc0(attn, x)
+        cases.append(dict(kind="mv", c=c, heads=heads, nv=nv, nf=nf, fs=fs, b=b, x=x, y=y0, w=w))
+        # ---- IP adapter (attn2 of the spatial transformers)
+        attn2 = Attention(c, cd, heads, dh)
+        procip = ap.IPAdapterXFormersAttnProcessor(hidden_size=c, cross_attention_dim=cd, num_tokens=(4,), scale=0.7)
+        text = torch.randn(b * nv * nf, 7, cd)
+        ipt = torch.randn(b * nv * nf, 1, 4, cd)
+        with torch.no_grad():
+            yip = procip(attn2, x, encoder_hidden_states=(text, [ipt]))
+        w2 = attn_weights(attn2, "a.attn2")
+        w2["a.attn2.processor.to_k_ip.0.weight"] = procip.to_k_ip[0].weight.detach().clone()
+        w2["a.attn2.processor.to_v_ip.0.weight"] = procip.to_v_ip[0].weight.detach().clone()
+        cases.append(dict(kind="ip", c=c, heads=heads, nv=nv, nf=nf, fs=fs, b=b, x=x, text=text, ip=ipt[:, 0], y=yip,
+                          w=w2, ip_scale=0.7))
+        # ---- SpatioTemporal (attn1/attn2 of the motion modules), released config
+        attn3 = Attention(c, None, heads, dh)
+        spatial_cfg = SimpleNamespace(enabled=True, attn_cfg=SimpleNamespace(
+            use_spatial_encoding=True, spatial_encoding_type="sinusoid", use_camera_encoding=False,
+            camera_encoding_type="sinusoid"))
+        image_cfg = SimpleNamespace(enabled=False)
+        procst = ap.SpatioTemporalI2VXFormersAttnProcessor(
+            hidden_size=c, feature_size=fs, num_views=nv, num_frames=nf, spatial_attn=spatial_cfg,
+            image_attn=image_cfg, use_alpha_blender=True)
+        with torch.no_grad():
+            procst.alpha_blender.mix_factor.fill_(0.3)
+        xt = torch.randn(b * nv * l, nf, c)
+        with torch.no_grad():
+            yst = procst(attn3, xt)
+        w3 = attn_weights(attn3, "m.attn1")
+        for n in ("to_q_sp", "to_k_sp", "to_v_sp", "to_out_sp"):
+            w3[f"m.attn1.processor.{n}.weight"] = getattr(procst, n).weight.detach().clone()
+        w3["m.attn1.processor.to_out_sp.bias"] = procst.to_out_sp.bias.detach().clone()
+        w3["m.attn1.processor.time_pos_embed.pe"] = procst.time_pos_embed.pe.detach().clone()
+        w3["m.attn1.processor.alpha_blender.mix_factor"] = procst.alpha_blender.mix_factor.detach().clone()
+        cases.append(dict(kind="st", c=c, heads=heads, nv=nv, nf=nf, fs=fs, b=b, x=xt, y=yst, w=w3,
+                          state_keys=sorted(procst.state_dict().keys())))
+    torch.save(cases, os.path.join(OUT, "ref_processors.pt"))
+
+    emb = {}
+    for (nfeat, h, w) in [(16, 4, 4), (160, 32, 32), (320, 16, 16), (640, 8, 8), (640, 4, 4)]:
+        m = SinePositionalEncoding2D(nfeat, normalize=True)
+        emb[(nfeat, h, w)] = m._forward(torch.zeros(1, h, w))[0].clone()
+    torch.save(emb, os.path.join(OUT, "ref_embeddings.pt"))
+
+    get_camera = load_camera_fns()
+    cam = {n: get_camera(n) for n in (1, 4, 8)}
+    torch.save(cam, os.path.join(OUT, "ref_camera.pt"))
+    print("wrote", [f for f in os.listdir(OUT) if f.endswith(".pt")])
+
+
+if __name__ == "__main__":
+    main()
