@@ -1,0 +1,449 @@
+// a3d_attention: O = softmax(scale * Q K^T) V, flash-style, on tcgen05 tensor cores with TMEM accumulators.
+//
+//   one CTA = one 128-row query tile of one (batch, head); 6 warps:
+//     warp 0      TMA producer (Q once, K/V tiles through a ring of smem stages; 128B-swizzled boxes read straight out
+//                 of the projection GEMM's output through rank-5 strided views -> the reference's
+//                 "(b n f) l c -> (b f) (n l) c" regroupings and frame-0 K/V broadcasts never materialise)
+//     warp 1      tcgen05.mma issuer:  S = Q K^T  (K-major A and B),  O += P V  (P K-major from smem, V MN-major)
+//     warps 2..5  softmax: one thread per query row reads S from TMEM, keeps the running max in the log2 domain, writes
+//                 fp16 P into swizzled smem, rescales O in TMEM only when the max moved by more than kRescaleLog2
+//   The row sum is not computed by the softmax warps: V carries a column of ones at index d (placed there by the
+//   projection epilogue), so O[:, d] accumulates sum(P) in fp32 alongside the PV product.
+//
+// Replaces xformers.ops.memory_efficient_attention at animatediff/models/attention_processor.py:103,233,268,405,416,656,691.
+#include "a3d_common.cuh"
+#include "a3d_host.cuh"
+
+namespace a3d {
+
+struct AttnDev {
+  int q_tiles, kv_tiles;
+  int rows_q, rows_k;            // valid rows per q tile / kv tile (<= 128)
+  int heads;
+  int q_t1, q_box1, q_box2, q_e3;
+  int k_t1, k_box1, k_box2, k_e3, kv_div, kv_i3_zero;
+  uint32_t q_box_bytes, k_box_bytes;   // bytes one 64-column TMA box delivers
+  float scale_log2;
+  __half* out;
+  int64_t os1, os2, os3, os4;
+  int accumulate;
+  float out_scale;
+};
+
+constexpr float kRescaleLog2 = 8.0f;
+
+template <int D>
+struct AttnCfg {
+  static constexpr int kDqk = (D + 15) / 16 * 16;        // 48 / 80 / 160
+  static constexpr int kDv = (D + 1 + 15) / 16 * 16;     // 48 / 96 / 176
+  static constexpr int kQBoxes = (kDqk + 63) / 64;       // 1 / 2 / 3
+  static constexpr int kVBoxes = (kDv + 63) / 64;        // 1 / 2 / 3
+  static constexpr int kStages = (D == 160) ? 1 : 2;
+  static constexpr int kBox = 128 * 128;                 // bytes of one 128-row x 64-col fp16 box
+  static constexpr int kSmemQ = kQBoxes * kBox;
+  static constexpr int kSmemK = kStages * kQBoxes * kBox;
+  static constexpr int kSmemV = kStages * kVBoxes * kBox;
+  static constexpr int kSmemP = 2 * kBox;
+  static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + 1024 + 256;
+  static constexpr int kTmemCols = (128 + kDv <= 256) ? 256 : 512;
+  static constexpr int kMinBlocks = (kSmemBytes <= 113 * 1024) ? 2 : 1;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, AttnCfg<D>::kMinBlocks)
+attn_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+               const __grid_constant__ CUtensorMap mapV) {
+  using Cfg = AttnCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kSmemQ;
+  uint8_t* sV = sK + Cfg::kSmemK;
+  uint8_t* sP = sV + Cfg::kSmemV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kSmemP);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;                     // [kStages]
+  uint64_t* v_full = k_full + Cfg::kStages;        // [kStages]
+  uint64_t* kv_empty = v_full + Cfg::kStages;      // [kStages]
+  uint64_t* s_full = kv_empty + Cfg::kStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int qt = blockIdx.x;
+  const int head = blockIdx.y;
+  const int qb = blockIdx.z;
+
+  if (p.rows_q < 128 || p.rows_k < 128) {
+    // partially filled tiles: rows TMA never writes must read as zeros (0 * garbage could be NaN in P V)
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    const int n16 = (Cfg::kSmemQ + Cfg::kSmemK + Cfg::kSmemV) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  // query / key coordinates
+  const int q_i1 = (qt % p.q_t1) * p.q_box1;
+  const int q_i2 = (qt / p.q_t1) * p.q_box2;
+  const int q_i3 = qb % p.q_e3;
+  const int q_i4 = qb / p.q_e3;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kb = qb / p.kv_div;
+      const int k_i3 = p.kv_i3_zero ? 0 : (kb % p.k_e3);
+      const int k_i4 = kb / p.k_e3;
+      mbar_expect_tx(q_full, p.q_box_bytes * Cfg::kQBoxes);
+#pragma unroll
+      for (int b = 0; b < Cfg::kQBoxes; ++b)
+        tma_load_5d(sQ + b * Cfg::kBox, &mapQ, q_full, head * Cfg::kDqk + b * 64, q_i1, q_i2, q_i3, q_i4);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        const int k_i1 = (j % p.k_t1) * p.k_box1;
+        const int k_i2 = (j / p.k_t1) * p.k_box2;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&k_full[stage], p.k_box_bytes * Cfg::kQBoxes);
+#pragma unroll
+        for (int b = 0; b < Cfg::kQBoxes; ++b)
+          tma_load_5d(sK + (stage * Cfg::kQBoxes + b) * Cfg::kBox, &mapK, &k_full[stage], head * Cfg::kDqk + b * 64, k_i1,
+                      k_i2, k_i3, k_i4);
+        mbar_expect_tx(&v_full[stage], p.k_box_bytes * Cfg::kVBoxes);
+#pragma unroll
+        for (int b = 0; b < Cfg::kVBoxes; ++b)
+          tma_load_5d(sV + (stage * Cfg::kVBoxes + b) * Cfg::kBox, &mapV, &v_full[stage], head * Cfg::kDv + b * 64, k_i1,
+                      k_i2, k_i3, k_i4);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        // ---- S = Q K^T
+        mbar_wait(&k_full[stage], phase);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < Cfg::kDqk / 16; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + (kk / 4) * Cfg::kBox) + (kk % 4) * 32, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(
+              smem_u32(sK + (stage * Cfg::kQBoxes + kk / 4) * Cfg::kBox) + (kk % 4) * 32, 16, 1024);
+          umma_f16(tmem_S, adesc, bdesc, idesc_qk, kk ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        // ---- O += P V
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[stage], phase);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + (kk / 4) * Cfg::kBox) + (kk % 4) * 32, 16, 1024);
+          // V is MN-major: 16 keys = two 8-row swizzle atoms (SBO = 1024 B); the next 64 value columns live one TMA
+          // box further (LBO = kBox)
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + stage * Cfg::kVBoxes * Cfg::kBox) + kk * 2048,
+                                                      Cfg::kBox, 1024);
+          umma_f16(tmem_O, adesc, bdesc, idesc_pv, (j | kk) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[stage]);
+        if (j == p.kv_tiles - 1) umma_commit(o_full);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                    // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    float m_run = -INFINITY;
+    for (int j = 0; j < p.kv_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // ---- pass 1: row max over the valid keys
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_addr + ch * 32, s);
+        tmem_wait_ld();
+        if (p.rows_k == 128) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (ch * 32 + i < p.rows_k) mx = fmaxf(mx, __uint_as_float(s[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      if (j == 0) {
+        m_run = m_new;
+      } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
+        const float alpha = exp2f(m_run - m_new);
+#pragma unroll 1
+        for (int c = 0; c < Cfg::kDv / 16; ++c) {
+          uint32_t o[16];
+          tmem_ld16(tmem_O + lane_addr + c * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tmem_O + lane_addr + c * 16, o);
+        }
+        tmem_wait_st();
+        m_run = m_new;
+      }
+      // ---- pass 2: P = exp2(s * scale_log2 - m_run) -> fp16 -> swizzled smem (K-major A operand of the PV product)
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_addr + ch * 32, s);
+        tmem_wait_ld();
+        uint8_t* pbox = sP + (ch >> 1) * Cfg::kBox;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 q;
+          __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int i = g * 8 + 2 * t;
+            float p0 = exp2f(__uint_as_float(s[i]) * p.scale_log2 - m_run);
+            float p1 = exp2f(__uint_as_float(s[i + 1]) * p.scale_log2 - m_run);
+            if (p.rows_k != 128) {
+              if (ch * 32 + i >= p.rows_k) p0 = 0.f;
+              if (ch * 32 + i + 1 >= p.rows_k) p1 = 0.f;
+            }
+            h[t] = __floats2half2_rn(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(pbox + sw128_offset(r, (ch & 1) * 4 + g)) = q;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / O[:, D] -> fp16 -> global (through the query view geometry)
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    float inv;
+    {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_addr + (D / 16) * 16, o);
+      tmem_wait_ld();
+      inv = p.out_scale / __uint_as_float(o[D % 16]);
+    }
+    const bool row_ok = r < p.rows_q;
+    const int i1 = q_i1 + r % p.q_box1;
+    const int i2 = q_i2 + r / p.q_box1;
+    __half* orow = p.out + (int64_t)i1 * p.os1 + (int64_t)i2 * p.os2 + (int64_t)q_i3 * p.os3 + (int64_t)q_i4 * p.os4 +
+                   head * D;
+#pragma unroll 1
+    for (int c = 0; c < (D + 15) / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_addr + c * 16, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c * 16 + g * 8 < D) {
+            uint4 q;
+            __half2* h = reinterpret_cast<__half2*>(&q);
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(o[g * 8 + t]) * inv;
+            if (p.accumulate) {
+              const uint4 old = *reinterpret_cast<const uint4*>(orow + c * 16 + g * 8);
+              const __half2* ho = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(ho[t]);
+                v[2 * t] += f.x;
+                v[2 * t + 1] += f.y;
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+            *reinterpret_cast<uint4*>(orow + c * 16 + g * 8) = q;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SIMT bring-up / reference kernel (one thread per (batch, head, query)); same view semantics, fp32 math
+// ---------------------------------------------------------------------------------------------------------------
+struct ViewDev {
+  const __half* base;
+  int64_t s1, s2, s3, s4;
+  int e1, e2, e3, e4;
+};
+
+__global__ void attn_simt_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, int64_t os1, int64_t os2, int64_t os3,
+                                 int64_t os4, int heads, int d, int dqk, int dv, float scale, int kv_div, int kv_i3_zero,
+                                 int accumulate, float out_scale) {
+  const int Lq = q.e1 * q.e2, Lk = k.e1 * k.e2;
+  const int64_t total = (int64_t)q.e3 * q.e4 * heads * Lq;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int l = (int)(idx % Lq);
+  const int h = (int)((idx / Lq) % heads);
+  const int qb = (int)(idx / ((int64_t)Lq * heads));
+  const int kb = qb / kv_div;
+  const __half* qp = q.base + (int64_t)(l % q.e1) * q.s1 + (int64_t)(l / q.e1) * q.s2 + (int64_t)(qb % q.e3) * q.s3 +
+                     (int64_t)(qb / q.e3) * q.s4 + h * dqk;
+  const int64_t koff = (int64_t)(kv_i3_zero ? 0 : kb % k.e3) * k.s3 + (int64_t)(kb / k.e3) * k.s4;
+  const int64_t voff = (int64_t)(kv_i3_zero ? 0 : kb % v.e3) * v.s3 + (int64_t)(kb / v.e3) * v.s4;
+  float m = -INFINITY;
+  for (int j = 0; j < Lk; ++j) {
+    const __half* kp = k.base + koff + (int64_t)(j % k.e1) * k.s1 + (int64_t)(j / k.e1) * k.s2 + h * dqk;
+    float s = 0.f;
+    for (int c = 0; c < d; ++c) s += __half2float(qp[c]) * __half2float(kp[c]);
+    m = fmaxf(m, s * scale);
+  }
+  float acc[160];
+  for (int c = 0; c < d; ++c) acc[c] = 0.f;
+  float sum = 0.f;
+  for (int j = 0; j < Lk; ++j) {
+    const __half* kp = k.base + koff + (int64_t)(j % k.e1) * k.s1 + (int64_t)(j / k.e1) * k.s2 + h * dqk;
+    const __half* vp = v.base + voff + (int64_t)(j % v.e1) * v.s1 + (int64_t)(j / v.e1) * v.s2 + h * dv;
+    float s = 0.f;
+    for (int c = 0; c < d; ++c) s += __half2float(qp[c]) * __half2float(kp[c]);
+    const float pj = expf(s * scale - m);
+    sum += pj;
+    for (int c = 0; c < d; ++c) acc[c] += pj * __half2float(vp[c]);
+  }
+  __half* op = out + (int64_t)(l % q.e1) * os1 + (int64_t)(l / q.e1) * os2 + (int64_t)(qb % q.e3) * os3 +
+               (int64_t)(qb / q.e3) * os4 + h * d;
+  for (int c = 0; c < d; ++c) {
+    float o = out_scale * acc[c] / sum;
+    if (accumulate) o += __half2float(op[c]);
+    op[c] = __float2half_rn(o);
+  }
+}
+
+static int tile_geom(const a3d_view5& v, int* box1, int* box2, int* t1, int* tiles, int* rows) {
+  if (v.e1 >= 128) {
+    if (v.e1 % 128) return fail(A3D_EINVAL, "a3d_attention: inner extent %d must be a multiple of 128", v.e1);
+    *box1 = 128; *box2 = 1; *t1 = v.e1 / 128; *tiles = *t1 * v.e2; *rows = 128;
+  } else {
+    int b2 = 128 / v.e1;
+    if (b2 > v.e2) b2 = v.e2;
+    if (b2 < 1 || v.e2 % b2) return fail(A3D_EINVAL, "a3d_attention: extents (%d,%d) do not tile", v.e1, v.e2);
+    *box1 = v.e1; *box2 = b2; *t1 = 1; *tiles = v.e2 / b2; *rows = v.e1 * b2;
+  }
+  return 0;
+}
+
+static int view_map(const a3d_view5& v, int box1, int box2, const CUtensorMap** out) {
+  const uint64_t dims[5] = {(uint64_t)v.cols, (uint64_t)v.e1, (uint64_t)v.e2, (uint64_t)v.e3, (uint64_t)v.e4};
+  const uint64_t str[4] = {(uint64_t)v.s1, (uint64_t)v.s2, (uint64_t)v.s3, (uint64_t)v.s4};
+  const uint32_t box[5] = {64, (uint32_t)box1, (uint32_t)box2, 1, 1};
+  MapKey k = make_key(v.base, dims, str, box);
+  return get_tensor_map(k, out);
+}
+
+template <int D>
+static int launch_attn(const AttnDev& dev, const CUtensorMap* mq, const CUtensorMap* mk, const CUtensorMap* mv, dim3 grid,
+                       cudaStream_t st) {
+  using Cfg = AttnCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  attn_tc_kernel<D><<<grid, 192, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+}  // namespace a3d
+
+extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
+  using namespace a3d;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!a || !a->q.base || !a->k.base || !a->v.base || !a->out) return fail(A3D_EINVAL, "a3d_attention: null operand");
+  const int d = a->d;
+  if (d != 40 && d != 80 && d != 160) return fail(A3D_EINVAL, "a3d_attention: head dim %d not in {40,80,160}", d);
+  if (a->k.e1 != a->v.e1 || a->k.e2 != a->v.e2 || a->k.e3 != a->v.e3 || a->k.e4 != a->v.e4)
+    return fail(A3D_EINVAL, "a3d_attention: K and V extents differ");
+  const int dqk = (d + 15) / 16 * 16, dv = (d + 1 + 15) / 16 * 16;
+  const int kv_div = a->kv_div > 0 ? a->kv_div : 1;
+  const int batches = a->q.e3 * a->q.e4;
+  if ((batches + kv_div - 1) / kv_div > a->k.e3 * a->k.e4 && !a->kv_i3_zero)
+    return fail(A3D_EINVAL, "a3d_attention: key batches (%d) do not cover query batches (%d / %d)", a->k.e3 * a->k.e4,
+                batches, kv_div);
+
+  if (a->impl == A3D_GEMM_SIMT) {
+    ViewDev q{reinterpret_cast<const __half*>(a->q.base), a->q.s1, a->q.s2, a->q.s3, a->q.s4, a->q.e1, a->q.e2, a->q.e3, a->q.e4};
+    ViewDev k{reinterpret_cast<const __half*>(a->k.base), a->k.s1, a->k.s2, a->k.s3, a->k.s4, a->k.e1, a->k.e2, a->k.e3, a->k.e4};
+    ViewDev v{reinterpret_cast<const __half*>(a->v.base), a->v.s1, a->v.s2, a->v.s3, a->v.s4, a->v.e1, a->v.e2, a->v.e3, a->v.e4};
+    const int64_t total = (int64_t)batches * a->heads * a->q.e1 * a->q.e2;
+    attn_simt_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(q, k, v, reinterpret_cast<__half*>(a->out), a->os1, a->os2,
+                                                                  a->os3, a->os4, a->heads, d, dqk, dv, a->scale, kv_div,
+                                                                  a->kv_i3_zero, a->accumulate,
+                                                                  a->out_scale == 0.f ? 1.f : a->out_scale);
+    A3D_LAUNCH_CHECK();
+    return A3D_OK;
+  }
+
+  AttnDev dev;
+  memset(&dev, 0, sizeof(dev));
+  int qb1, qb2, qt1, qtiles, qrows, kb1, kb2, kt1, ktiles, krows;
+  if (int r = tile_geom(a->q, &qb1, &qb2, &qt1, &qtiles, &qrows)) return r;
+  if (int r = tile_geom(a->k, &kb1, &kb2, &kt1, &ktiles, &krows)) return r;
+  dev.q_tiles = qtiles; dev.kv_tiles = ktiles; dev.rows_q = qrows; dev.rows_k = krows;
+  dev.heads = a->heads;
+  dev.q_t1 = qt1; dev.q_box1 = qb1; dev.q_box2 = qb2; dev.q_e3 = a->q.e3;
+  dev.k_t1 = kt1; dev.k_box1 = kb1; dev.k_box2 = kb2; dev.k_e3 = a->k.e3;
+  dev.kv_div = kv_div; dev.kv_i3_zero = a->kv_i3_zero;
+  dev.q_box_bytes = 128u * qrows; dev.k_box_bytes = 128u * krows;
+  dev.scale_log2 = a->scale * 1.4426950408889634f;
+  dev.out = reinterpret_cast<__half*>(a->out);
+  dev.os1 = a->os1; dev.os2 = a->os2; dev.os3 = a->os3; dev.os4 = a->os4;
+  dev.accumulate = a->accumulate;
+  dev.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
+  if ((a->os1 | a->os2 | a->os3 | a->os4) % 8 || (reinterpret_cast<uintptr_t>(a->out) & 15))
+    return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
+  const CUtensorMap *mq, *mk, *mv;
+  if (int r = view_map(a->q, qb1, qb2, &mq)) return r;
+  if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
+  if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
+  dim3 grid(qtiles, a->heads, batches);
+  if (batches > 65535 || a->heads > 65535) return fail(A3D_EINVAL, "a3d_attention: grid too large");
+  switch (d) {
+    case 40: return launch_attn<40>(dev, mq, mk, mv, grid, st);
+    case 80: return launch_attn<80>(dev, mq, mk, mv, grid, st);
+    default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
+  }
+}

@@ -1,0 +1,475 @@
+// a3d_gemm: C = epilogue(A * B^T) on 5th-gen tensor cores.
+//   * persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = epilogue
+//   * operands staged by TMA into 128B-swizzled shared memory (K-major), accumulators double-buffered in TMEM so the
+//     epilogue of tile i overlaps the main loop of tile i+1
+//   * A3D_A_CONV3: the A operand is an implicit 3x3 im2col of an NHWC image -- each k-block is one (tap, 64-channel)
+//     slice fetched with a rank-4 TMA box whose out-of-bounds rows/cols are zero-filled by the hardware (= padding 1);
+//     stride-2 convolutions use the tensor map's traversal strides
+// Replaces torch linear/conv2d (cuBLAS/cuDNN) under the diffusers blocks driven by
+// animatediff/models/unet_motion_mv_model.py:768-859 of the reference.
+#include "a3d_common.cuh"
+#include "a3d_host.cuh"
+
+namespace a3d {
+
+struct GemmDev {
+  int64_t M, N, K;
+  int num_k_blocks;
+  int tiles_m, tiles_n;
+  // conv A addressing
+  int a_mode;
+  int cpb;        // 64-channel blocks per tap (C/64)
+  int conv_s;     // stride
+  int tpi;        // output tiles per image (>=1) or 0 when several images share a tile
+  int boh;        // output rows per tile
+  int bimg;       // images per tile
+  // epilogue
+  const float* bias;
+  const float* rowbias;
+  int64_t rb_ld, rb_div, rb_mod;
+  float acc_scale;
+  const __half* R1; int64_t ldr1; float r1_scale;
+  const __half* R2; int64_t ldr2;
+  void* C; int64_t ldc;
+  int geglu, out_f32;
+  int64_t perm_a, perm_b;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ int64_t perm_row(int64_t m, int64_t a, int64_t b) {
+  if (a == 0) return m;
+  const int64_t ab = a * b;
+  return (m / ab) * ab + (m % b) * a + (m / b) % a;
+}
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 160 ? 5 : 6);
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
+        int img0 = 0, oh0 = 0;
+        if (p.a_mode == A3D_A_CONV3) {
+          if (p.tpi > 0) { img0 = mt / p.tpi; oh0 = (mt % p.tpi) * p.boh; }
+          else { img0 = mt * p.bimg; oh0 = 0; }
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.a_mode == A3D_A_CONV3) {
+            const int tap = kb / p.cpb, c0 = (kb % p.cpb) * kBK;
+            const int ky = tap / 3, kx = tap % 3;
+            tma_load_5d(smem_a + stage * Cfg::kABytes, &mapA, &full_bar[stage], c0, kx - 1, oh0 * p.conv_s + ky - 1, img0, 0);
+          } else {
+            tma_load_5d(smem_a + stage * Cfg::kABytes, &mapA, &full_bar[stage], kb * kBK, mt * kBM, 0, 0, 0);
+          }
+          tma_load_5d(smem_b + stage * Cfg::kBBytes, &mapB, &full_bar[stage], kb * kBK, nt * BN, 0, 0, 0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(kBM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 halves (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)mt * kBM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int64_t orow = row_ok ? perm_row(row, p.perm_a, p.perm_b) : 0;
+      const int64_t rbrow = (p.rowbias && row_ok) ? ((row / p.rb_div) % p.rb_mod) : 0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      if (!p.geglu) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_wait_ld();
+          const int64_t col0 = (int64_t)nt * BN + ch * 32;
+          if (row_ok && col0 < p.N) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            const bool full = col0 + 32 <= p.N;
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+            }
+            if (p.rowbias) {
+              const float* rb = p.rowbias + rbrow * p.rb_ld + col0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (full || col0 + i < p.N) v[i] += __ldg(rb + i);
+            }
+            if (p.acc_scale != 1.0f) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
+            }
+            if (p.R1) {
+              const __half* r1 = p.R1 + row * p.ldr1 + col0;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 q = __ldg(reinterpret_cast<const uint4*>(r1) + i);
+                  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    v[i * 8 + 2 * j] += p.r1_scale * f.x;
+                    v[i * 8 + 2 * j + 1] += p.r1_scale * f.y;
+                  }
+                }
+              } else {
+                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) v[i] += p.r1_scale * __half2float(r1[i]);
+              }
+            }
+            if (p.R2) {
+              const __half* r2 = p.R2 + orow * p.ldr2 + col0;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 q = __ldg(reinterpret_cast<const uint4*>(r2) + i);
+                  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    v[i * 8 + 2 * j] += f.x;
+                    v[i * 8 + 2 * j + 1] += f.y;
+                  }
+                }
+              } else {
+                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) v[i] += __half2float(r2[i]);
+              }
+            }
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.C) + orow * p.ldc + col0;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              } else {
+                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = v[i];
+              }
+            } else {
+              __half* o = reinterpret_cast<__half*>(p.C) + orow * p.ldc + col0;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint4 q;
+                  __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i * 8 + 2 * j], v[i * 8 + 2 * j + 1]);
+                  reinterpret_cast<uint4*>(o)[i] = q;
+                }
+              } else {
+                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = __float2half_rn(v[i]);
+              }
+            }
+          }
+        }
+      } else {
+        // GEGLU: column blocks come as (u[32] | g[32]); bias only
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 64; ++ch) {
+          uint32_t ru[32], rg[32];
+          tmem_ld32(taddr + ch * 64, ru);
+          tmem_ld32(taddr + ch * 64 + 32, rg);
+          tmem_wait_ld();
+          const int64_t col0 = (int64_t)nt * BN + ch * 64;
+          if (row_ok && col0 < p.N) {
+            __half* o = reinterpret_cast<__half*>(p.C) + orow * p.ldc + col0 / 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 q;
+              __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = i * 8 + 2 * j;
+                float u0 = __uint_as_float(ru[e]), u1 = __uint_as_float(ru[e + 1]);
+                float g0 = __uint_as_float(rg[e]), g1 = __uint_as_float(rg[e + 1]);
+                if (p.bias) {
+                  u0 += __ldg(p.bias + col0 + e); u1 += __ldg(p.bias + col0 + e + 1);
+                  g0 += __ldg(p.bias + col0 + 32 + e); g1 += __ldg(p.bias + col0 + 32 + e + 1);
+                }
+                h[j] = __floats2half2_rn(u0 * gelu_erf(g0), u1 * gelu_erf(g1));
+              }
+              reinterpret_cast<uint4*>(o)[i] = q;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SIMT bring-up / reference kernel: same semantics, one thread per output element (also serves odd shapes)
+// ---------------------------------------------------------------------------------------------------------------
+struct SimtConv { int n, h, w, c, s, oh, ow; };
+
+__global__ void gemm_simt_kernel(const GemmDev p, const __half* __restrict__ A, int64_t lda, const __half* __restrict__ B,
+                                 SimtConv cv) {
+  const int64_t n_out = p.geglu ? p.N / 2 : p.N;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.M * n_out) return;
+  const int64_t m = idx / n_out;
+  const int64_t j = idx % n_out;
+  auto dot = [&](int64_t n) {
+    float acc = 0.f;
+    const __half* b = B + n * p.K;
+    if (p.a_mode == A3D_A_PLAIN) {
+      const __half* a = A + m * lda;
+      for (int64_t k = 0; k < p.K; ++k) acc += __half2float(a[k]) * __half2float(b[k]);
+    } else {
+      const int img = (int)(m / (cv.oh * cv.ow));
+      const int oy = (int)((m / cv.ow) % cv.oh), ox = (int)(m % cv.ow);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int iy = oy * cv.s + tap / 3 - 1, ix = ox * cv.s + tap % 3 - 1;
+        if (iy < 0 || iy >= cv.h || ix < 0 || ix >= cv.w) continue;
+        const __half* a = A + (((int64_t)img * cv.h + iy) * cv.w + ix) * cv.c;
+        const __half* bb = b + (int64_t)tap * cv.c;
+        for (int c = 0; c < cv.c; ++c) acc += __half2float(a[c]) * __half2float(bb[c]);
+      }
+    }
+    return acc;
+  };
+  const int64_t orow = perm_row(m, p.perm_a, p.perm_b);
+  if (p.geglu) {
+    const int64_t blk = j / 32, e = j % 32;
+    const int64_t nu = blk * 64 + e, ng = nu + 32;
+    float u = dot(nu), g = dot(ng);
+    if (p.bias) { u += p.bias[nu]; g += p.bias[ng]; }
+    reinterpret_cast<__half*>(p.C)[orow * p.ldc + j] = __float2half_rn(u * gelu_erf(g));
+    return;
+  }
+  float v = dot(j);
+  if (p.bias) v += p.bias[j];
+  if (p.rowbias) v += p.rowbias[((m / p.rb_div) % p.rb_mod) * p.rb_ld + j];
+  v *= p.acc_scale;
+  if (p.R1) v += p.r1_scale * __half2float(p.R1[m * p.ldr1 + j]);
+  if (p.R2) v += __half2float(p.R2[orow * p.ldr2 + j]);
+  if (p.out_f32) reinterpret_cast<float*>(p.C)[orow * p.ldc + j] = v;
+  else reinterpret_cast<__half*>(p.C)[orow * p.ldc + j] = __float2half_rn(v);
+}
+
+template <int BN>
+static int launch_tc(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = dev.tiles_m * dev.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(dev, *mapA, *mapB);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+}  // namespace a3d
+
+extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
+  using namespace a3d;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!a || !a->A || !a->B || !a->C) return fail(A3D_EINVAL, "a3d_gemm: null operand");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return fail(A3D_EINVAL, "a3d_gemm: empty problem M=%lld N=%lld K=%lld",
+                                                        (long long)a->M, (long long)a->N, (long long)a->K);
+  GemmDev d;
+  memset(&d, 0, sizeof(d));
+  d.M = a->M; d.N = a->N; d.K = a->K;
+  d.a_mode = a->a_mode;
+  d.bias = a->bias; d.rowbias = a->rowbias; d.rb_ld = a->rb_ld;
+  d.rb_div = a->rb_div > 0 ? a->rb_div : 1; d.rb_mod = a->rb_mod > 0 ? a->rb_mod : (int64_t)1 << 40;
+  d.acc_scale = a->acc_scale == 0.f ? 1.f : a->acc_scale;
+  d.R1 = reinterpret_cast<const __half*>(a->R1); d.ldr1 = a->ldr1; d.r1_scale = a->r1_scale;
+  d.R2 = reinterpret_cast<const __half*>(a->R2); d.ldr2 = a->ldr2;
+  d.C = a->C; d.ldc = a->ldc; d.geglu = a->geglu; d.out_f32 = a->out_f32;
+  d.perm_a = a->perm_a; d.perm_b = a->perm_b;
+  if (a->geglu && (a->rowbias || a->R1 || a->R2 || a->out_f32 || a->perm_a || (a->N % 64)))
+    return fail(A3D_EINVAL, "a3d_gemm: GEGLU epilogue supports bias only and needs N %% 64 == 0");
+
+  SimtConv cv{0, 0, 0, 0, 1, 0, 0};
+  if (a->a_mode == A3D_A_CONV3) {
+    const int s = a->conv_stride;
+    if (s != 1 && s != 2) return fail(A3D_EINVAL, "a3d_gemm: conv stride must be 1 or 2");
+    if (a->conv_h % s || a->conv_w % s) return fail(A3D_EINVAL, "a3d_gemm: conv H/W must be multiples of the stride");
+    cv = SimtConv{a->conv_n, a->conv_h, a->conv_w, a->conv_c, s, a->conv_h / s, a->conv_w / s};
+    if (a->K != 9LL * a->conv_c || a->M != (int64_t)cv.n * cv.oh * cv.ow)
+      return fail(A3D_EINVAL, "a3d_gemm: conv geometry does not match M/K");
+    d.conv_s = s;
+  } else if (a->a_mode != A3D_A_PLAIN) {
+    return fail(A3D_EINVAL, "a3d_gemm: unknown a_mode %d", a->a_mode);
+  }
+
+  // ---- can the tensor-core path take it?
+  bool tc_ok = (a->K % kBK == 0) && ((reinterpret_cast<uintptr_t>(a->A) & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(a->B) & 15) == 0) && (a->ldc % 8 == 0) &&
+               ((reinterpret_cast<uintptr_t>(a->C) & 15) == 0);
+  if (a->a_mode == A3D_A_PLAIN) tc_ok = tc_ok && (a->lda % 8 == 0) && a->lda >= a->K;
+  int boh = 0, bimg = 1, tpi = 0;
+  if (a->a_mode == A3D_A_CONV3) {
+    tc_ok = tc_ok && (cv.c % kBK == 0);
+    const int opix = cv.oh * cv.ow;
+    if (opix >= kBM) {
+      tc_ok = tc_ok && (opix % kBM == 0) && (kBM % cv.ow == 0);
+      boh = kBM / cv.ow; tpi = opix / kBM; bimg = 1;
+    } else {
+      tc_ok = tc_ok && (kBM % opix == 0);
+      boh = cv.oh; tpi = 0; bimg = kBM / (opix > 0 ? opix : 1);
+    }
+    tc_ok = tc_ok && cv.ow * cv.s <= 256 && boh * cv.s <= 256;
+  }
+  if (a->R1) tc_ok = tc_ok && (a->ldr1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a->R1) & 15) == 0);
+  if (a->R2) tc_ok = tc_ok && (a->ldr2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a->R2) & 15) == 0);
+  int impl = a->impl;
+  if (impl == A3D_GEMM_AUTO) impl = tc_ok ? A3D_GEMM_TCGEN05 : A3D_GEMM_SIMT;
+  if (impl == A3D_GEMM_TCGEN05 && !tc_ok)
+    return fail(A3D_EINVAL, "a3d_gemm: shape/alignment not supported by the tcgen05 path (M=%lld N=%lld K=%lld)",
+                (long long)a->M, (long long)a->N, (long long)a->K);
+
+  if (impl == A3D_GEMM_SIMT) {
+    const int64_t n_out = a->geglu ? a->N / 2 : a->N;
+    const int64_t total = a->M * n_out;
+    const int threads = 128;
+    const int64_t blocks = (total + threads - 1) / threads;
+    gemm_simt_kernel<<<(unsigned)blocks, threads, 0, st>>>(d, reinterpret_cast<const __half*>(a->A), a->lda,
+                                                           reinterpret_cast<const __half*>(a->B), cv);
+    A3D_LAUNCH_CHECK();
+    return A3D_OK;
+  }
+
+  // ---- tile shape
+  int BN;
+  if (a->geglu) BN = (a->N % 256 == 0) ? 256 : 128;
+  else if (a->N % 256 == 0) BN = 256;
+  else if (a->N % 160 == 0) BN = 160;
+  else BN = 128;
+  if (a->geglu && a->N % BN) return fail(A3D_EINVAL, "a3d_gemm: GEGLU needs N %% 128 == 0");
+  d.num_k_blocks = (int)(a->K / kBK);
+  d.tiles_m = (int)((a->M + kBM - 1) / kBM);
+  d.tiles_n = (int)((a->N + BN - 1) / BN);
+  d.cpb = a->a_mode == A3D_A_CONV3 ? cv.c / kBK : 0;
+  d.tpi = tpi; d.boh = boh; d.bimg = bimg;
+
+  const CUtensorMap *mapA = nullptr, *mapB = nullptr;
+  {
+    MapKey kb;
+    const uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)a->N, 1, 1, 1};
+    const uint64_t str[4] = {(uint64_t)a->K, (uint64_t)a->K * a->N, (uint64_t)a->K * a->N, (uint64_t)a->K * a->N};
+    const uint32_t box[5] = {kBK, (uint32_t)BN, 1, 1, 1};
+    kb = make_key(a->B, dims, str, box);
+    if (int r = get_tensor_map(kb, &mapB)) return r;
+  }
+  if (a->a_mode == A3D_A_PLAIN) {
+    const uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)a->M, 1, 1, 1};
+    const uint64_t str[4] = {(uint64_t)a->lda, (uint64_t)a->lda * a->M, (uint64_t)a->lda * a->M, (uint64_t)a->lda * a->M};
+    const uint32_t box[5] = {kBK, kBM, 1, 1, 1};
+    MapKey ka = make_key(a->A, dims, str, box);
+    if (int r = get_tensor_map(ka, &mapA)) return r;
+  } else {
+    const uint64_t img = (uint64_t)cv.h * cv.w * cv.c;
+    const uint64_t dims[5] = {(uint64_t)cv.c, (uint64_t)cv.w, (uint64_t)cv.h, (uint64_t)cv.n, 1};
+    const uint64_t str[4] = {(uint64_t)cv.c, (uint64_t)cv.w * cv.c, img, img * cv.n};
+    const uint32_t box[5] = {kBK, (uint32_t)(cv.ow * cv.s), (uint32_t)(boh * cv.s), (uint32_t)bimg, 1};
+    MapKey ka = make_key(a->A, dims, str, box);
+    ka.estr[1] = cv.s; ka.estr[2] = cv.s;
+    if (int r = get_tensor_map(ka, &mapA)) return r;
+  }
+  switch (BN) {
+    case 256: return launch_tc<256>(d, mapA, mapB, st);
+    case 160: return launch_tc<160>(d, mapA, mapB, st);
+    default: return launch_tc<128>(d, mapA, mapB, st);
+  }
+}

@@ -1,0 +1,482 @@
+// HBM-bound companions of the tensor-core kernels: GroupNorm(+SiLU) on NHWC (incl. the over-frames variant of the motion
+// modules), LayerNorm, temporal (F x F) attention, conv_in / conv_out with the reference's layout changes folded in,
+// small fp32 linears for the embeddings, nearest upsample, DDIM+CFG update.  All loads/stores are 16-byte vectors on the
+// channel-contiguous (token-major) layout.
+#include "a3d_common.cuh"
+#include "a3d_host.cuh"
+
+namespace a3d {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ int64_t perm_row2(int64_t m, int64_t a, int64_t b) {
+  if (a == 0) return m;
+  const int64_t ab = a * b;
+  return (m / ab) * ab + (m % b) * a + (m / b) % a;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// stats: grid (chunks, samples); block = C/8 threads (one uint4 = 8 channels per thread), loops over the chunk's rows.
+__global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
+                                int64_t rows_per_sample, int rows_per_chunk, int groups, float* __restrict__ stats) {
+  extern __shared__ float sm[];  // [2 * groups]
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int sample = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+  int64_t r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int c0 = threadIdx.x * 8;
+  if (c0 < C) {
+    const __half* src = (c0 < c1) ? x1 : x2;
+    const int cc = (c0 < c1) ? c0 : c0 - c1;
+    const int ld = (c0 < c1) ? c1 : c2;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    for (int64_t r = r0; r < r1; ++r) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)sample * rows_per_sample + r) * ld + cc));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c0 + i) / cpg;
+      atomicAdd(&sm[2 * g], s[i]);
+      atomicAdd(&sm[2 * g + 1], q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(int64_t)sample * 2 * groups + i], sm[i]);
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
+                                int64_t total_rows, int64_t rows_per_sample, int groups, float eps, int silu,
+                                int64_t perm_a, int64_t perm_b, const float* __restrict__ stats) {
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int vec_per_row = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_rows * vec_per_row) return;
+  const int64_t row = idx / vec_per_row;
+  const int c0 = (int)(idx % vec_per_row) * 8;
+  const int64_t sample = row / rows_per_sample;
+  const float inv_n = 1.0f / (float)(rows_per_sample * cpg);
+  const __half* src = (c0 < c1) ? x1 + row * c1 + c0 : x2 + row * c2 + (c0 - c1);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  uint4 o;
+  __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    float r[2] = {f.x, f.y};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = c0 + 2 * i + j;
+      const int g = c / cpg;
+      const float mean = stats[(sample * groups + g) * 2] * inv_n;
+      const float var = fmaxf(stats[(sample * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+      float t = (r[j] - mean) * rsqrtf(var + eps) * __ldg(gamma + c) + __ldg(beta + c);
+      if (silu) t = silu_f(t);
+      r[j] = t;
+    }
+    ho[i] = __floats2half2_rn(r[0], r[1]);
+  }
+  const int64_t orow = perm_row2(row, perm_a, perm_b);
+  *reinterpret_cast<uint4*>(y + orow * C + c0) = o;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+__global__ void layer_norm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, __half* __restrict__ y, int64_t rows, int C, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  constexpr int kMaxIter = 5;  // C <= 1280
+  float v[kMaxIter * 8];
+  float s = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int i = lane + it * 32;
+    if (i < nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * C) + i);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        v[it * 8 + 2 * j] = f.x; v[it * 8 + 2 * j + 1] = f.y;
+        s += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int i = lane + it * 32;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[it * 8 + j] - mean; q += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int i = lane + it * 32;
+    if (i < nvec) {
+      uint4 o;
+      __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = i * 8 + 2 * j;
+        const float a = (v[it * 8 + 2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        const float b = (v[it * 8 + 2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+        ho[j] = __floats2half2_rn(a, b);
+      }
+      *(reinterpret_cast<uint4*>(y + row * C) + i) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ temporal attention
+// one block per pixel; thread = (head, query frame).  Q/K/V rows of the pixel are staged in shared memory; all queries of
+// a head read the same K/V address -> shared-memory broadcast.
+__global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int frames, int heads, int d,
+                                     float scale) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __half* s = reinterpret_cast<__half*>(smraw);
+  const int C = heads * d;
+  const int64_t pix = blockIdx.x;
+  const int nvec = frames * 3 * C / 8;
+  const uint4* src = reinterpret_cast<const uint4*>(qkv + pix * frames * 3 * C);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<uint4*>(s)[i] = __ldg(src + i);
+  __syncthreads();
+  const int f = threadIdx.x % frames;
+  const int h = threadIdx.x / frames;
+  if (h >= heads) return;
+  const __half* q = s + f * 3 * C + h * d;
+  float sc[32];
+  float mx = -INFINITY;
+  for (int j = 0; j < frames; ++j) {
+    const __half* k = s + j * 3 * C + C + h * d;
+    float acc = 0.f;
+    for (int c = 0; c < d; c += 8) {
+      const uint4 qa = *reinterpret_cast<const uint4*>(q + c);
+      const uint4 ka = *reinterpret_cast<const uint4*>(k + c);
+      const __half2* qh = reinterpret_cast<const __half2*>(&qa);
+      const __half2* kh = reinterpret_cast<const __half2*>(&ka);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 a = __half22float2(qh[t]), b = __half22float2(kh[t]);
+        acc += a.x * b.x + a.y * b.y;
+      }
+    }
+    sc[j] = acc * scale;
+    mx = fmaxf(mx, sc[j]);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < frames; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.0f / sum;
+  __half* o = out + (pix * frames + f) * C + h * d;
+  for (int c = 0; c < d; c += 8) {
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    for (int j = 0; j < frames; ++j) {
+      const uint4 va = *reinterpret_cast<const uint4*>(s + j * 3 * C + 2 * C + h * d + c);
+      const __half2* vh = reinterpret_cast<const __half2*>(&va);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 b = __half22float2(vh[t]);
+        acc[2 * t] += sc[j] * b.x;
+        acc[2 * t + 1] += sc[j] * b.y;
+      }
+    }
+    uint4 ov;
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+    *reinterpret_cast<uint4*>(o + c) = ov;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ misc elementwise
+__global__ void upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ y, int64_t n, int h, int w, int c) {
+  const int vec = c / 8;
+  const int64_t total = n * (2 * h) * (2 * w) * vec;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = (int)(idx % vec);
+  const int64_t pix = idx / vec;
+  const int ox = (int)(pix % (2 * w));
+  const int oy = (int)((pix / (2 * w)) % (2 * h));
+  const int64_t img = pix / ((int64_t)4 * h * w);
+  const uint4 val = __ldg(reinterpret_cast<const uint4*>(x + ((img * h + oy / 2) * w + ox / 2) * c) + v);
+  *(reinterpret_cast<uint4*>(y + pix * c) + v) = val;
+}
+
+__global__ void silu_rows_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t rows, int c, int rep) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * c) return;
+  const int64_t r = idx / c;
+  const int j = (int)(idx % c);
+  y[idx] = __float2half_rn(silu_f(x[(r / rep) * c + j]));
+}
+
+__global__ void timestep_proj_kernel(const float* __restrict__ t, float* __restrict__ out, int rows, int half) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * half) return;
+  const int r = idx / half, i = idx % half;
+  const float freq = expf(-9.210340371976184f * (float)i / (float)half);   // ln(10000)
+  const float e = t[r] * freq;
+  out[r * 2 * half + i] = cosf(e);           // flip_sin_to_cos=True -> [cos | sin]
+  out[r * 2 * half + half + i] = sinf(e);
+}
+
+__global__ void linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                  float* __restrict__ y, int m, int n, int k, int act_in, int accumulate) {
+  // one warp per output element
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (int64_t)m * n) return;
+  const int r = (int)(wid / n), j = (int)(wid % n);
+  float acc = 0.f;
+  for (int i = lane; i < k; i += 32) {
+    float xv = x[(int64_t)r * k + i];
+    if (act_in == 1) xv = silu_f(xv);
+    acc += xv * w[(int64_t)j * k + i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (b) acc += b[j];
+    if (accumulate) acc += y[(int64_t)r * n + j];
+    y[(int64_t)r * n + j] = acc;
+  }
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, int64_t n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) y[idx] = __float2half_rn(x[idx]);
+}
+
+// conv_in: sample [BN, Cin, F, H, W] fp32 -> y NHWC fp16 [(BN F) H W, Cout]
+__global__ void conv_in_kernel(const float* __restrict__ sample, const float* __restrict__ w, const float* __restrict__ b,
+                               __half* __restrict__ y, int bn, int cin, int f, int h, int wd, int cout) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)bn * f * h * wd * cout;
+  if (idx >= total) return;
+  const int co = (int)(idx % cout);
+  const int64_t pix = idx / cout;
+  const int x = (int)(pix % wd), yy = (int)((pix / wd) % h);
+  const int fr = (int)((pix / ((int64_t)wd * h)) % f);
+  const int s = (int)(pix / ((int64_t)wd * h * f));
+  float acc = b[co];
+  for (int ci = 0; ci < cin; ++ci) {
+    const float* img = sample + (((int64_t)s * cin + ci) * f + fr) * h * wd;
+    const float* wk = w + ((int64_t)co * cin + ci) * 9;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = x + kx - 1;
+        if (ix < 0 || ix >= wd) continue;
+        acc += img[iy * wd + ix] * wk[ky * 3 + kx];
+      }
+    }
+  }
+  y[idx] = __float2half_rn(acc);
+}
+
+// conv_out: x NHWC fp16 [(BN F) H W, Cin] -> y [BN, Cout, F, H, W] fp32 ; one warp per pixel, cout <= 8
+__global__ void conv_out_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                float* __restrict__ y, int bn, int cin, int f, int h, int wd, int cout) {
+  const int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t npix = (int64_t)bn * f * h * wd;
+  if (pix >= npix) return;
+  const int px = (int)(pix % wd), py = (int)((pix / wd) % h);
+  const int64_t img = pix / ((int64_t)wd * h);   // (bn f)
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+    if (iy < 0 || iy >= h || ix < 0 || ix >= wd) continue;
+    const __half* src = x + ((img * h + iy) * wd + ix) * cin;
+    for (int c = lane; c < cin; c += 32) {
+      const float v = __half2float(src[c]);
+      for (int o = 0; o < cout; ++o) acc[o] += v * __ldg(w + ((int64_t)o * cin + c) * 9 + tap);
+    }
+  }
+  for (int o = 0; o < cout; ++o) {
+    float a = acc[o];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) {
+      const int fr = (int)(img % f);
+      const int64_t smp = img / f;
+      y[(((smp * cout + o) * f + fr) * h + py) * wd + px] = a + b[o];
+    }
+  }
+}
+
+__global__ void ddim_cfg_step_kernel(float* __restrict__ lat, const float* __restrict__ eps2, const float* __restrict__ first,
+                                     int bn, int c, int f, int hw, float g, float a_t, float a_prev, int uncond_first) {
+  const int64_t n = (int64_t)bn * c * f * hw;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int fr = (int)((idx / hw) % f);
+  if (fr == 0 && first) {
+    const int64_t sc = idx / ((int64_t)f * hw);  // (bn c)
+    lat[idx] = first[sc * hw + idx % hw];
+    return;
+  }
+  const float e0 = eps2[idx], e1 = eps2[n + idx];
+  const float eps = uncond_first ? (e0 + g * (e1 - e0)) : (e0 + g * (e0 - e1));
+  const float x = lat[idx];
+  const float x0 = (x - sqrtf(1.f - a_t) * eps) / sqrtf(a_t);
+  lat[idx] = sqrtf(a_prev) * x0 + sqrtf(1.f - a_prev) * eps;
+}
+
+}  // namespace a3d
+
+using namespace a3d;
+
+extern "C" int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* y,
+                              int64_t samples, int64_t rows_per_sample, int groups, float eps, int silu, int64_t perm_a,
+                              int64_t perm_b, float* ws_stats, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int C = c1 + (x2 ? c2 : 0);
+  if (!x2) c2 = 0;
+  if (C % groups || C % 8 || c1 % 8 || c2 % 8 || C / 8 > 1024 || groups > 64)
+    return fail(A3D_EINVAL, "a3d_group_norm: unsupported channels C=%d (c1=%d c2=%d) groups=%d", C, c1, c2, groups);
+  A3D_CUDA_CHECK(cudaMemsetAsync(ws_stats, 0, sizeof(float) * 2 * groups * samples, st));
+  const int rows_per_chunk = 64;
+  dim3 grid((unsigned)((rows_per_sample + rows_per_chunk - 1) / rows_per_chunk), (unsigned)samples);
+  const int threads = ((C / 8 + 31) / 32) * 32;
+  gn_stats_kernel<<<grid, threads, 2 * groups * sizeof(float), st>>>(reinterpret_cast<const __half*>(x1), c1,
+                                                                     reinterpret_cast<const __half*>(x2), c2, rows_per_sample,
+                                                                     rows_per_chunk, groups, ws_stats);
+  A3D_LAUNCH_CHECK();
+  const int64_t total = samples * rows_per_sample * (C / 8);
+  gn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __half*>(x1), c1, reinterpret_cast<const __half*>(x2), c2, gamma, beta,
+      reinterpret_cast<__half*>(y), samples * rows_per_sample, rows_per_sample, groups, eps, silu, perm_a, perm_b, ws_stats);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int c, float eps,
+                              void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (c % 8 || c > 1280) return fail(A3D_EINVAL, "a3d_layer_norm: C=%d must be a multiple of 8 and <= 1280", c);
+  const int warps = 8;
+  layer_norm_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(
+      reinterpret_cast<const __half*>(x), gamma, beta, reinterpret_cast<__half*>(y), rows, c, eps);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, int heads, int d, float scale,
+                                 void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (frames > 32 || frames * heads > 1024 || d % 8) return fail(A3D_EINVAL, "a3d_temporal_attn: frames=%d heads=%d d=%d", frames, heads, d);
+  const size_t smem = (size_t)frames * 3 * heads * d * 2;
+  static size_t max_set = 0;
+  if (smem > 48 * 1024 && smem > max_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_set = smem;
+  }
+  const int threads = ((frames * heads + 31) / 32) * 32;
+  temporal_attn_kernel<<<(unsigned)pixels, threads, smem, st>>>(reinterpret_cast<const __half*>(qkv),
+                                                                reinterpret_cast<__half*>(out), frames, heads, d, scale);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_upsample2x(const void* x, void* y, int64_t n, int h, int w, int c, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (c % 8) return fail(A3D_EINVAL, "a3d_upsample2x: C %% 8");
+  const int64_t total = n * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x),
+                                                                    reinterpret_cast<__half*>(y), n, h, w, c);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_silu_rows(const float* x, void* y, int64_t rows, int c, int rep, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = rows * c;
+  silu_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, reinterpret_cast<__half*>(y), rows, c, rep);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_conv_in(const float* sample, const float* w, const float* b, void* y, int bn, int cin, int f, int h,
+                           int wd, int cout, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)bn * f * h * wd * cout;
+  conv_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sample, w, b, reinterpret_cast<__half*>(y), bn, cin, f, h, wd, cout);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_conv_out(const void* x, const float* w, const float* b, float* y, int bn, int cin, int f, int h, int wd,
+                            int cout, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cout > 8) return fail(A3D_EINVAL, "a3d_conv_out: cout <= 8");
+  const int64_t npix = (int64_t)bn * f * h * wd;
+  conv_out_kernel<<<(unsigned)((npix * 32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x), w, b, y, bn, cin, f, h, wd, cout);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_timestep_proj(const float* t, float* out, int rows, int half, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  timestep_proj_kernel<<<(rows * half + 127) / 128, 128, 0, st>>>(t, out, rows, half);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_linear_f32(const float* x, const float* w, const float* b, float* y, int m, int n, int k, int act_in,
+                              int accumulate, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t threads = (int64_t)m * n * 32;
+  linear_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, w, b, y, m, n, k, act_in, accumulate);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_cast_f32_f16(const float* x, void* y, int64_t n, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cast_f32_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, reinterpret_cast<__half*>(y), n);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_ddim_cfg_step(float* latents, const float* noise_pred, const float* first_frame, int bn, int c, int f,
+                                 int hw, float guidance, float alpha_t, float alpha_prev, int uncond_first, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n = (int64_t)bn * c * f * hw;
+  ddim_cfg_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(latents, noise_pred, first_frame, bn, c, f, hw, guidance,
+                                                                   alpha_t, alpha_prev, uncond_first);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}

@@ -1,0 +1,192 @@
+/* animate3d_b200 -- C ABI of the B200-native hot path (liba3d.so).
+ *
+ * Plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host.  All entry points
+ * enqueue work on `stream` (a cudaStream_t passed as void*) and return 0 on success or a negative A3D_E* code; the
+ * message of the last failure on the calling thread is available from a3d_last_error().  Nothing here allocates
+ * device memory: the caller owns every buffer (workspace sizes are queried first), which is what makes the whole
+ * UNet forward capturable in one CUDA graph.
+ *
+ * Which reference interface each entry point replaces (reference = yanqinJiang/Animate3D @ 033a1be):
+ *   a3d_gemm            torch.nn.functional.linear / conv2d (cuBLAS / cuDNN) under diffusers ResnetBlock2D, Transformer2DModel,
+ *                       TransformerTemporalModel, FeedForward/GEGLU -- called from animatediff/models/unet_motion_mv_model.py:768-859
+ *   a3d_attention       xformers.ops.memory_efficient_attention at animatediff/models/attention_processor.py:103,233,268,405,416,656,691
+ *   a3d_temporal_attn   Attention.get_attention_scores + torch.bmm at animatediff/models/attention_processor.py:634-635
+ *   a3d_group_norm      torch GroupNorm(+SiLU) in ResnetBlock2D / Transformer2DModel / TransformerTemporalModel (5-D, over frames)
+ *   a3d_layer_norm      torch LayerNorm in BasicTransformerBlock
+ *   a3d_conv_in/out     unet_motion_mv_model.py:767-768 (permute + conv_in) and 859-862 (conv_out + permute back)
+ *   a3d_ddim_cfg_step   animatediff/pipelines/pipeline.py:1023-1031 (CFG combine + DDIMScheduler.step + frame-0 re-injection)
+ *   a3d_raster_*        diff_gaussian_rasterization._C.rasterize_gaussians / rasterize_gaussians_backward, called at
+ *                       custom/threestudio-animate3d/renderer/diff_gaussian_rasterizer_advanced_4d.py:161-170
+ */
+#ifndef A3D_H_
+#define A3D_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3D_OK 0
+#define A3D_EINVAL (-1)   /* bad argument / unsupported shape */
+#define A3D_ECUDA (-2)    /* CUDA runtime or driver error     */
+#define A3D_ENOTSUP (-3)  /* device is not sm_100             */
+
+const char* a3d_last_error(void);
+int a3d_version(void);
+/* 0 when the current device is sm_100 and the driver entry points needed for TMA are available. */
+int a3d_init(void);
+
+/* ---------------------------------------------------------------- GEMM / implicit-GEMM convolution ----------- */
+/* C[M,N] = epilogue( A[M,K] * B[N,K]^T ), fp16 operands, fp32 accumulation in tensor memory (tcgen05).
+ * A operand modes: A3D_A_PLAIN  row-major [M, lda]
+ *                  A3D_A_CONV3  NHWC image [n_img, H, W, C] gathered as a 3x3 (pad 1, stride 1|2) im2col, K = 9*C,
+ *                               k index = (ky*3+kx)*C + c ; M = n_img*OH*OW
+ * Epilogue:  v = acc + bias[n] + rowbias[((m / rb_div) % rb_mod) * rb_ld + n]
+ *            v = acc_scale * v + r1_scale * R1[m, n] + R2[om, n]          (om = permuted output row, see below)
+ *            GEGLU: columns come in interleaved blocks of 32 (u | g); out[.., j] = u_j * gelu_erf(g_j), N_out = N/2
+ *            out[om, n] stored as fp16 (or fp32 when out_f32)
+ * Row permutation (perm_a, perm_b > 0): om = (m / (a*b))*(a*b) + (m % b)*a + (m / b) % a   ("(x a b) -> (x b a)").
+ */
+enum { A3D_A_PLAIN = 0, A3D_A_CONV3 = 1 };
+enum { A3D_GEMM_AUTO = 0, A3D_GEMM_TCGEN05 = 1, A3D_GEMM_SIMT = 2 };
+
+typedef struct a3d_gemm_args {
+  const void* A;      /* fp16 */
+  const void* B;      /* fp16 weights [N, K], K contiguous */
+  void* C;            /* fp16 (or fp32) output */
+  int64_t M, N, K;
+  int64_t lda, ldc;   /* elements; lda ignored for CONV3 */
+  int a_mode;
+  int conv_n, conv_h, conv_w, conv_c, conv_stride; /* CONV3 geometry (input) */
+  const float* bias;          /* [N] or NULL */
+  const float* rowbias;       /* [rb_rows, rb_ld] or NULL */
+  int64_t rb_ld, rb_div, rb_mod;
+  float acc_scale;            /* 1.0 if unused */
+  const void* R1; int64_t ldr1; float r1_scale;   /* fp16 or NULL */
+  const void* R2; int64_t ldr2;                   /* fp16 or NULL */
+  int geglu;
+  int out_f32;
+  int64_t perm_a, perm_b;     /* 0,0 = identity */
+  int impl;                   /* A3D_GEMM_* */
+} a3d_gemm_args;
+
+int a3d_gemm(const a3d_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------- fused attention (tcgen05) ------------------ */
+/* O = softmax(scale * Q K^T) V per (batch, head); Q/K/V are read in place from projection outputs through rank-5
+ * strided views so that the reference's "(b n f) l c -> (b f) (n l) c" regroupings never materialise.
+ * A view addresses element (col, i1, i2, i3, i4) at base + col + i1*s1 + i2*s2 + i3*s3 + i4*s4 (element strides).
+ * The sequence index l of a (batch) is l = i2*e1 + i1 (i1 < e1, i2 < e2); the batch index is qb = i4*e3 + i3.
+ * Keys: batch kb = qb / kv_div; i3 is forced to 0 when kv_i3_zero (frame-0 keys of the I2V branch).
+ * Head h reads Q/K columns [h*dqk, h*dqk+dqk) (dqk = roundup16(d), zero padded by the projection) and V columns
+ * [h*dv, h*dv+dv) with dv = roundup16(d+1) whose column d holds 1.0 (the row sum then falls out of the PV product).
+ * Output: fp16 [.., heads*d] written through the same view geometry as Q with row stride ldo:
+ *   out = (accumulate ? out : 0) + out_scale * O.
+ */
+typedef struct a3d_view5 {
+  const void* base;
+  int64_t s1, s2, s3, s4;   /* element strides of dims 1..4 (dim 0 = columns, stride 1) */
+  int64_t cols;             /* extent of dim 0 (total columns addressable from base) */
+  int32_t e1, e2, e3, e4;   /* extents of dims 1..4 */
+} a3d_view5;
+
+typedef struct a3d_attn_args {
+  a3d_view5 q, k, v;        /* k and v share extents */
+  void* out;                /* fp16 */
+  int64_t os1, os2, os3, os4; /* element strides of the output rows (same extents as q) */
+  int heads, d;             /* true head dim (40/80/160) */
+  float scale;
+  int kv_div, kv_i3_zero;
+  int accumulate; float out_scale;
+  int impl;                 /* A3D_GEMM_AUTO / _TCGEN05 / _SIMT */
+} a3d_attn_args;
+
+int a3d_attention(const a3d_attn_args* args, void* stream);
+
+/* Temporal attention over F frames for every (pixel, head): qkv [P, F, 3*C] fp16 (q | k | v), out [P, F, C]. */
+int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, int heads, int d, float scale, void* stream);
+
+/* ---------------------------------------------------------------- normalisation / elementwise ---------------- */
+/* GroupNorm over (rows_per_sample x C/groups) per sample, NHWC fp16.  x = concat(x1[C1], x2[C2]) along channels
+ * (x2 may be NULL).  Optional SiLU.  Output rows may be permuted (perm_a, perm_b as in a3d_gemm). */
+int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* y,
+                   int64_t samples, int64_t rows_per_sample, int groups, float eps, int silu, int64_t perm_a,
+                   int64_t perm_b, float* ws_stats, void* stream);
+/* LayerNorm over C per row. */
+int a3d_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int c, float eps,
+                   void* stream);
+/* nearest x2 upsample NHWC */
+int a3d_upsample2x(const void* x, void* y, int64_t n, int h, int w, int c, void* stream);
+/* y[r, :] = silu(x[r / rep, :]) as fp16 (time-embedding broadcast for the time_emb_proj GEMM) */
+int a3d_silu_rows(const float* x, void* y, int64_t rows, int c, int rep, void* stream);
+/* conv_in: sample [BN, Cin, F, H, W] (fp32) -> NHWC fp16 [(BN F), H, W, Cout], 3x3 pad 1; w [Cout, Cin, 3, 3] fp32 */
+int a3d_conv_in(const float* sample, const float* w, const float* b, void* y, int bn, int cin, int f, int h, int wd,
+                int cout, void* stream);
+/* conv_out: NHWC fp16 [(BN F), H, W, Cin] -> [BN, Cout, F, H, W] fp32 */
+int a3d_conv_out(const void* x, const float* w, const float* b, float* y, int bn, int cin, int f, int h, int wd,
+                 int cout, void* stream);
+/* sinusoidal timestep projection + 2-layer MLP inputs: out[r, :] = [cos(t_r f_i), sin(t_r f_i)] fp32, dim = 2*half */
+int a3d_timestep_proj(const float* t, float* out, int rows, int half, void* stream);
+/* small fp32 linear: y[M,N] = act(x[M,K]) W[N,K]^T + b  (act: 0 none, 1 silu);  add: y += previous y when accumulate */
+int a3d_linear_f32(const float* x, const float* w, const float* b, float* y, int m, int n, int k, int act_in,
+                   int accumulate, void* stream);
+/* fp32 -> fp16 cast with optional LayerNorm-free copy (utility) */
+int a3d_cast_f32_f16(const float* x, void* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- scheduler ---------------------------------- */
+/* One DDIM (eta=0) update with classifier-free guidance and frame-0 re-injection (pipeline.py:1023-1031):
+ *   eps = e_a + g * (e_b - e_a)   with (e_a, e_b) = (uncond, cond) halves of noise_pred when uncond_first, else the
+ *   guidance ordering eps = e_text + g*(e_text - e_uncond);  x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t);
+ *   x' = sqrt(a_prev) x0 + sqrt(1-a_prev) eps;  frame 0 of x' := first_frame.
+ * latents/noise_pred: fp32 [BN(,x2), C, F, H, W]. */
+int a3d_ddim_cfg_step(float* latents, const float* noise_pred, const float* first_frame, int bn, int c, int f, int hw,
+                      float guidance, float alpha_t, float alpha_prev, int uncond_first, void* stream);
+
+/* ---------------------------------------------------------------- 4D-Gaussian rasterizer --------------------- */
+typedef struct a3d_raster_cam {
+  float viewmatrix[16];   /* row-vector convention, as passed by threestudio/utils/ops.py:344-359 */
+  float projmatrix[16];
+  float campos[3];
+  float tanfovx, tanfovy;
+} a3d_raster_cam;
+
+typedef struct a3d_raster_args {
+  int P;                     /* gaussians */
+  int H, W;
+  int num_cams;              /* cameras rendered by this call (batched) */
+  const a3d_raster_cam* cams;/* device array [num_cams] */
+  const float* means3D;      /* [cam_stride_geom ? num_cams : 1][P,3] */
+  const float* scales;       /* [..][P,3] */
+  const float* rotations;    /* [..][P,4] */
+  const float* opacities;    /* [P,1] */
+  const float* shs;          /* [P,(deg+1)^2,3] or NULL */
+  const float* colors_precomp; /* [P,3] or NULL */
+  int sh_degree, sh_coeffs;
+  int per_cam_geometry;      /* 1: means/scales/rotations have a leading camera dim */
+  float scale_modifier;
+  float bg[3];
+} a3d_raster_args;
+
+/* workspace bytes for a forward with at most max_rendered (tile,gaussian) pairs per camera */
+size_t a3d_raster_workspace_bytes(int P, int H, int W, int num_cams, int64_t max_rendered);
+/* forward: color [cams,3,H,W], depth [cams,1,H,W], alpha [cams,1,H,W], radii [cams,P] int32.
+ * num_rendered_host (pinned, [cams]) receives the pair counts; returns A3D_EINVAL if a camera overflowed max_rendered. */
+int a3d_raster_forward(const a3d_raster_args* args, float* color, float* depth, float* alpha, int32_t* radii,
+                       void* workspace, size_t workspace_bytes, int64_t max_rendered, int64_t* num_rendered_host,
+                       void* stream);
+/* backward: grads w.r.t. means3D/scales/rotations ([cams or 1][P,*], accumulated over cameras when geometry is shared),
+ * opacities [P,1], colors/shs, means2D [cams,P,3]. Needs the workspace of the matching forward untouched. */
+int a3d_raster_backward(const a3d_raster_args* args, const float* dL_dcolor, const float* dL_ddepth,
+                        const float* dL_dalpha, const float* alpha, const int32_t* radii, void* workspace,
+                        size_t workspace_bytes, int64_t max_rendered, float* dL_dmeans3D, float* dL_dscales,
+                        float* dL_drotations, float* dL_dopacity, float* dL_dcolors, float* dL_dshs,
+                        float* dL_dmeans2D, void* stream);
+/* debug/parity taps of the binning stage for one camera: sorted keys [n] uint64, point_list [n] uint32, ranges [tiles] uint2 */
+int a3d_raster_binning_tap(const void* workspace, int P, int H, int W, int num_cams, int64_t max_rendered, int cam,
+                           uint64_t* keys_out, uint32_t* point_list_out, uint32_t* ranges_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3D_H_ */
