@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdint.h>
 
 namespace a3d {

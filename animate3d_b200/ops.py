@@ -19,6 +19,7 @@ def _chk16(*ts):
 
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int = 0, ldc: int = 0,
          conv: Optional[Tuple[int, int, int, int, int]] = None, bias=None, rowbias=None, rb_div: int = 1, rb_mod: int = 0,
+         rb_ld: int = 0,
          acc_scale: float = 1.0, R1=None, ldr1: int = 0, r1_scale: float = 1.0, R2=None, ldr2: int = 0, geglu: bool = False,
          out_f32: bool = False, perm: Tuple[int, int] = (0, 0), impl: int = L.IMPL_AUTO) -> torch.Tensor:
     """out = epilogue(A @ B^T); see a3d_gemm in include/a3d.h.  `conv` = (n_img, H, W, C, stride) selects the implicit
@@ -37,7 +38,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
         a.a_mode = L.A_PLAIN
     a.bias = L.ptr(bias)
     a.rowbias = L.ptr(rowbias)
-    a.rb_ld = rowbias.shape[-1] if rowbias is not None else 0
+    a.rb_ld = (rb_ld or rowbias.stride(0)) if rowbias is not None else 0
     a.rb_div, a.rb_mod = rb_div, rb_mod
     a.acc_scale = acc_scale
     a.R1, a.ldr1, a.r1_scale = L.ptr(R1), ldr1 or N, r1_scale
