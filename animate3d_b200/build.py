@@ -13,7 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liba3d.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["a3d_api.cu", "a3d_gemm.cu", "a3d_attn.cu", "a3d_ops.cu", "a3d_raster.cu"]
+SOURCES = ["a3d_api.cu", "a3d_gemm.cu", "a3d_attn.cu", "a3d_ops.cu", "a3d_raster.cu", "a3d_raster_pre.cu"]
+# index-defining rasterizer arithmetic must not be contracted into FMAs (bit parity with oracle/raster_oracle.py)
+EXTRA = {"a3d_raster_pre.cu": ["--fmad=false"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
@@ -41,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -124,12 +124,15 @@ def preprocess(means3D, scales, rotations, opacities, shs, colors_precomp, sh_de
     projx, projy = hx * p_w, hy * p_w
 
     cov3 = cov3d_from_scale_rot(scales, rotations, scale_modifier)
-    focal_x = W / (2.0 * tanfovx)
-    focal_y = H / (2.0 * tanfovy)
-    limx, limy = 1.3 * tanfovx, 1.3 * tanfovy
+    # the C ABI carries tanfov as float32; all derived constants are float32 operations
+    tfx = torch.tensor(float(tanfovx), dtype=f32)
+    tfy = torch.tensor(float(tanfovy), dtype=f32)
+    focal_x = W / (2.0 * tfx)
+    focal_y = H / (2.0 * tfy)
+    limx, limy = 1.3 * tfx, 1.3 * tfy
     tzs = torch.where(in_front, tz, torch.ones_like(tz))     # keep culled lanes finite
-    txc = torch.clamp(tx / tzs, min=-limx, max=limx) * tzs
-    tyc = torch.clamp(ty / tzs, min=-limy, max=limy) * tzs
+    txc = torch.minimum(limx, torch.maximum(-limx, tx / tzs)) * tzs
+    tyc = torch.minimum(limy, torch.maximum(-limy, ty / tzs)) * tzs
     j00 = focal_x / tzs
     j02 = -(focal_x * txc) / (tzs * tzs)
     j11 = focal_y / tzs
@@ -245,7 +248,9 @@ def render(pre: Preprocessed, point_list: np.ndarray, ranges: np.ndarray, H: int
         dx = xy[:, 0:1] - pxf
         dy = xy[:, 1:2] - pyf
         power = -0.5 * (co[:, 0:1] * dx * dx + co[:, 2:3] * dy * dy) - co[:, 1:2] * dx * dy
-        a = torch.clamp(co[:, 3:4] * torch.exp(power), max=0.99)
+        a_raw = co[:, 3:4] * torch.exp(power)
+        # min(0.99, .) with a pass-through gradient: upstream's backward ignores the clamp
+        a = a_raw + (torch.clamp(a_raw, max=0.99) - a_raw).detach()
         live = (power <= 0) & (a >= 1.0 / 255.0)
         a = torch.where(live, a, torch.zeros_like(a))
         T_after = torch.cumprod(1.0 - a, dim=0)
