@@ -118,10 +118,11 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     from animate3d_b200.flops import unet_forward_flops
     from animate3d_b200.unet_config import UNetConfig
-    ocfg = O.UNetConfig(num_views=1, num_frames=4)
+    nf = 1 if os.environ.get("A3D_BENCH_TINY") else 4
+    ocfg = O.UNetConfig(num_views=1, num_frames=nf)
     sd = O.make_state_dict(ocfg, 0)
-    sample, text, camera, img = O.synthetic_inputs(ocfg, 1, 1, 4, 0)
-    fl = unet_forward_flops(UNetConfig(), 1, 1, 4)["total"]
+    sample, text, camera, img = O.synthetic_inputs(ocfg, 1, 1, nf, 0)
+    fl = unet_forward_flops(UNetConfig(), 1, 1, nf)["total"]
     with torch.no_grad():
         for _ in range(args.warmup):
             O.unet_forward(sd, ocfg, sample, 500, text, camera, img, 1)
@@ -130,7 +131,7 @@ def run_reference(args, rank, world):
             O.unet_forward(sd, ocfg, sample, 500, text, camera, img, 1)
         dt = (time.perf_counter() - t0) / args.steps
     val = (fl / dt) / sf
-    sample_desc = (f"each step = one fp32 oracle forward of 1 view x 4 frames x 32x32x4 ({fl / 1e12:.2f} TFLOP of the "
+    sample_desc = (f"each step = one fp32 oracle forward of 1 view x {nf} frames x 32x32x4 ({fl / 1e12:.2f} TFLOP of the "
                    f"{sf / 1e12:.2f} TFLOP CFG step); steps/s extrapolated by FLOPs")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
