@@ -11,6 +11,8 @@
 //   projection epilogue), so O[:, d] accumulates sum(P) in fp32 alongside the PV product.
 //
 // Replaces xformers.ops.memory_efficient_attention at animatediff/models/attention_processor.py:103,233,268,405,416,656,691.
+#include <stdlib.h>
+
 #include "a3d_common.cuh"
 #include "a3d_host.cuh"
 
@@ -194,8 +196,13 @@ attn_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const 
         tmem_ld32(tmem_S + lane_addr + ch * 32, s);
         tmem_wait_ld();
         if (p.rows_k == 128) {
+          float mx1 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+          for (int i = 0; i < 32; i += 4) {
+            mx = fmax3(mx, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          }
+          mx = fmaxf(mx, mx1);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) if (ch * 32 + i < p.rows_k) mx = fmaxf(mx, __uint_as_float(s[i]));
@@ -205,7 +212,7 @@ attn_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const 
       if (j == 0) {
         m_run = m_new;
       } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
-        const float alpha = exp2f(m_run - m_new);
+        const float alpha = ex2_approx(m_run - m_new);
 #pragma unroll 1
         for (int c = 0; c < Cfg::kDv / 16; ++c) {
           uint32_t o[16];
@@ -232,8 +239,8 @@ attn_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const 
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int i = g * 8 + 2 * t;
-            float p0 = exp2f(__uint_as_float(s[i]) * p.scale_log2 - m_run);
-            float p1 = exp2f(__uint_as_float(s[i + 1]) * p.scale_log2 - m_run);
+            float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_run));
+            float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_run));
             if (p.rows_k != 128) {
               if (ch * 32 + i >= p.rows_k) p0 = 0.f;
               if (ch * 32 + i + 1 >= p.rows_k) p1 = 0.f;
@@ -298,6 +305,314 @@ attn_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2 (head_dim 40): TWO 128-row query tiles per CTA sharing every K/V tile; 10 warps:
+//   warp 0 TMA, warp 1 MMA issuer, warps 2..5 softmax group 0 (S0/P0/O0), warps 6..9 softmax group 1 (S1/P1/O1).
+//   The MMA warp alternates  PV0(j) -> QK0(j+1) -> PV1(j) -> QK1(j+1)  so the tensor pipe works on one tile while the
+//   other tile's softmax runs (8 softmax warps = 2 per SM sub-partition keep the MUFU pipe fed).
+//   Softmax math per element: 1 FFMA (scale & subtract max), 1 MUFU.EX2, 1/2 F2FP pack, 1/2 FMNMX3.
+// ---------------------------------------------------------------------------------------------------------------
+template <int D>
+struct Attn2Cfg {
+  static constexpr int kDqk = (D + 15) / 16 * 16;
+  static constexpr int kDv = (D + 1 + 15) / 16 * 16;
+  static constexpr int kQBoxes = (kDqk + 63) / 64;
+  static constexpr int kVBoxes = (kDv + 63) / 64;
+  static constexpr int kStages = 2;
+  static constexpr int kBox = 128 * 128;
+  static constexpr int kSmemQ = 2 * kQBoxes * kBox;
+  static constexpr int kSmemK = kStages * kQBoxes * kBox;
+  static constexpr int kSmemV = kStages * kVBoxes * kBox;
+  static constexpr int kSmemP = 2 * 2 * kBox;
+  static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + 1024 + 256;
+  static constexpr int kOStride = 64;   // TMEM columns reserved per O accumulator
+  static_assert(kDv <= kOStride, "v2 kernel is specialised for small head dims");
+};
+
+template <int D>
+__global__ void __launch_bounds__(320, 1)
+attn2_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                const __grid_constant__ CUtensorMap mapV) {
+  using Cfg = Attn2Cfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                       // [2 tiles][kQBoxes]
+  uint8_t* sK = sQ + Cfg::kSmemQ;
+  uint8_t* sV = sK + Cfg::kSmemK;
+  uint8_t* sP = sV + Cfg::kSmemV;           // [2 tiles][2 boxes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kSmemP);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + Cfg::kStages;
+  uint64_t* kv_empty = v_full + Cfg::kStages;
+  uint64_t* s_full = kv_empty + Cfg::kStages;   // [2]
+  uint64_t* p_full = s_full + 2;                 // [2]
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt0 = blockIdx.x * 2;
+  const bool has1 = qt0 + 1 < p.q_tiles;
+  const int head = blockIdx.y;
+  const int qb = blockIdx.z;
+
+  if (p.rows_q < 128 || p.rows_k < 128 || !has1) {
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    const int n16 = (Cfg::kSmemQ + Cfg::kSmemK + Cfg::kSmemV) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4);
+    }
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int q_i3 = qb % p.q_e3;
+  const int q_i4 = qb / p.q_e3;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kb = qb / p.kv_div;
+      const int k_i3 = p.kv_i3_zero ? 0 : (kb % p.k_e3);
+      const int k_i4 = kb / p.k_e3;
+      mbar_expect_tx(q_full, p.q_box_bytes * Cfg::kQBoxes * (has1 ? 2 : 1));
+      for (int t = 0; t < (has1 ? 2 : 1); ++t) {
+        const int qt = qt0 + t;
+        const int q_i1 = (qt % p.q_t1) * p.q_box1, q_i2 = (qt / p.q_t1) * p.q_box2;
+#pragma unroll
+        for (int b = 0; b < Cfg::kQBoxes; ++b)
+          tma_load_5d(sQ + (t * Cfg::kQBoxes + b) * Cfg::kBox, &mapQ, q_full, head * Cfg::kDqk + b * 64, q_i1, q_i2, q_i3, q_i4);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        const int k_i1 = (j % p.k_t1) * p.k_box1;
+        const int k_i2 = (j / p.k_t1) * p.k_box2;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&k_full[stage], p.k_box_bytes * Cfg::kQBoxes);
+#pragma unroll
+        for (int b = 0; b < Cfg::kQBoxes; ++b)
+          tma_load_5d(sK + (stage * Cfg::kQBoxes + b) * Cfg::kBox, &mapK, &k_full[stage], head * Cfg::kDqk + b * 64, k_i1,
+                      k_i2, k_i3, k_i4);
+        mbar_expect_tx(&v_full[stage], p.k_box_bytes * Cfg::kVBoxes);
+#pragma unroll
+        for (int b = 0; b < Cfg::kVBoxes; ++b)
+          tma_load_5d(sV + (stage * Cfg::kVBoxes + b) * Cfg::kBox, &mapV, &v_full[stage], head * Cfg::kDv + b * 64, k_i1,
+                      k_i2, k_i3, k_i4);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
+      auto issue_qk = [&](int g, int stage) {
+#pragma unroll
+        for (int kk = 0; kk < Cfg::kDqk / 16; ++kk) {
+          const uint64_t adesc =
+              make_smem_desc_sw128(smem_u32(sQ + (g * Cfg::kQBoxes + kk / 4) * Cfg::kBox) + (kk % 4) * 32, 16, 1024);
+          const uint64_t bdesc =
+              make_smem_desc_sw128(smem_u32(sK + (stage * Cfg::kQBoxes + kk / 4) * Cfg::kBox) + (kk % 4) * 32, 16, 1024);
+          umma_f16(tmem_base + g * 128, adesc, bdesc, idesc_qk, kk ? 1u : 0u);
+        }
+        umma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, int stage, int j) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + (g * 2 + kk / 4) * Cfg::kBox) + (kk % 4) * 32, 16, 1024);
+          const uint64_t bdesc =
+              make_smem_desc_sw128(smem_u32(sV + stage * Cfg::kVBoxes * Cfg::kBox) + kk * 2048, Cfg::kBox, 1024);
+          umma_f16(tmem_base + 256 + g * Cfg::kOStride, adesc, bdesc, idesc_pv, (j | kk) ? 1u : 0u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      if (has1) issue_qk(1, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == Cfg::kStages) { nstage = 0; nphase ^= 1; }
+        const bool more = j + 1 < p.kv_tiles;
+        // ---- tile 0
+        mbar_wait(&p_full[0], j & 1);
+        mbar_wait(&v_full[stage], phase);
+        tc_fence_after();
+        issue_pv(0, stage, j);
+        if (more) {
+          mbar_wait(&k_full[nstage], nphase);
+          tc_fence_after();
+          issue_qk(0, nstage);
+        }
+        // ---- tile 1
+        if (has1) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          issue_pv(1, stage, j);
+        }
+        umma_commit(&kv_empty[stage]);
+        if (has1 && more) issue_qk(1, nstage);
+        stage = nstage;
+        phase = nphase;
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    if (g == 0 || has1) {
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+      const uint32_t tmem_S = tmem_base + g * 128;
+      const uint32_t tmem_O = tmem_base + 256 + g * Cfg::kOStride;
+      uint8_t* sPg = sP + g * 2 * Cfg::kBox;
+      float m_run = -INFINITY;
+      const bool masked = p.rows_k != 128;
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        // ---- pass 1: row max
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t s[64];
+          tmem_ld64(tmem_S + lane_addr + hf * 64, s);
+          tmem_wait_ld();
+          if (!masked) {
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+              mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) if (hf * 64 + i < p.rows_k) mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          }
+        }
+        const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
+        if (j == 0) {
+          m_run = m_new;
+        } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
+          const float alpha = ex2_approx(m_run - m_new);
+#pragma unroll 1
+          for (int c = 0; c < Cfg::kDv / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_addr + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_addr + c * 16, o);
+          }
+          tmem_wait_st();
+          m_run = m_new;
+        }
+        // ---- pass 2: P = exp2(s * c - m) -> fp16 -> swizzled smem
+        const float neg_m = -m_run;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t s[64];
+          tmem_ld64(tmem_S + lane_addr + hf * 64, s);
+          tmem_wait_ld();
+          uint8_t* pbox = sPg + hf * Cfg::kBox;
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {
+            uint4 q;
+            uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = c16 * 8 + 2 * t;
+              float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m));
+              float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m));
+              if (masked) {
+                if (hf * 64 + i >= p.rows_k) p0 = 0.f;
+                if (hf * 64 + i + 1 >= p.rows_k) p1 = 0.f;
+              }
+              qw[t] = pack_f16x2(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(pbox + sw128_offset(r, c16)) = q;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+      // ---- epilogue
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      float inv;
+      {
+        uint32_t o[16];
+        tmem_ld16(tmem_O + lane_addr + (D / 16) * 16, o);
+        tmem_wait_ld();
+        inv = p.out_scale / __uint_as_float(o[D % 16]);
+      }
+      const int qt = qt0 + g;
+      const int q_i1 = (qt % p.q_t1) * p.q_box1, q_i2 = (qt / p.q_t1) * p.q_box2;
+      const bool row_ok = r < p.rows_q;
+      const int i1 = q_i1 + r % p.q_box1;
+      const int i2 = q_i2 + r / p.q_box1;
+      __half* orow = p.out + (int64_t)i1 * p.os1 + (int64_t)i2 * p.os2 + (int64_t)q_i3 * p.os3 + (int64_t)q_i4 * p.os4 + head * D;
+#pragma unroll 1
+      for (int c = 0; c < (D + 15) / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tmem_O + lane_addr + c * 16, o);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            if (c * 16 + gq * 8 < D) {
+              uint4 q;
+              __half2* h = reinterpret_cast<__half2*>(&q);
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(o[gq * 8 + t]) * inv;
+              if (p.accumulate) {
+                const uint4 old = *reinterpret_cast<const uint4*>(orow + c * 16 + gq * 8);
+                const __half2* ho = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(ho[t]);
+                  v[2 * t] += f.x;
+                  v[2 * t + 1] += f.y;
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+              *reinterpret_cast<uint4*>(orow + c * 16 + gq * 8) = q;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -387,6 +702,30 @@ static int launch_attn(const AttnDev& dev, const CUtensorMap* mq, const CUtensor
   return A3D_OK;
 }
 
+template <int D>
+static int launch_attn2(const AttnDev& dev, const CUtensorMap* mq, const CUtensorMap* mk, const CUtensorMap* mv, dim3 grid,
+                        cudaStream_t st) {
+  using Cfg = Attn2Cfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn2_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  grid.x = (grid.x + 1) / 2;
+  attn2_tc_kernel<D><<<grid, 320, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+static int attn_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("A3D_ATTN_VARIANT");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 }  // namespace a3d
 
 extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
@@ -442,7 +781,7 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   dim3 grid(qtiles, a->heads, batches);
   if (batches > 65535 || a->heads > 65535) return fail(A3D_EINVAL, "a3d_attention: grid too large");
   switch (d) {
-    case 40: return launch_attn<40>(dev, mq, mk, mv, grid, st);
+    case 40: return attn_variant() == 1 ? launch_attn<40>(dev, mq, mk, mv, grid, st) : launch_attn2<40>(dev, mq, mk, mv, grid, st);
     case 80: return launch_attn<80>(dev, mq, mk, mv, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
   }

@@ -53,7 +53,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStageOut = 4 * 4096;   // per-epilogue-warp 32 x 128 B staging tile
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -64,7 +65,8 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStageOut);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -152,19 +154,111 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // TMEM -> registers (one accumulator row per thread) -> bias / row-bias / scale in fp32 -> fp16 -> per-warp swizzled
+    // staging tile in shared memory -> coalesced phase: 8 (or 4) lanes cover one 128 B (64 B) row segment, residuals are
+    // read and the result written as full lines.  (Per-thread-row stores wrote 16 B slivers of 32 different lines per
+    // instruction and ran the output at < 0.7 TB/s.)
+    const int quad = warp & 3;
+    uint8_t* stg = smem_stage + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int64_t row = (int64_t)mt * kBM + quad * 32 + lane;
+      const int64_t row0 = (int64_t)mt * kBM + quad * 32;
+      const int64_t row = row0 + lane;
       const bool row_ok = row < p.M;
-      const int64_t orow = row_ok ? perm_row(row, p.perm_a, p.perm_b) : 0;
       const int64_t rbrow = (p.rowbias && row_ok) ? ((row / p.rb_div) % p.rb_mod) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      if (!p.geglu) {
+      const int64_t n_out = p.geglu ? p.N / 2 : p.N;
+
+      // coalesced write-out of `ncols` (32 or 64) staged fp16 columns starting at output column `ocol0`
+      auto flush = [&](int ncols, int64_t ocol0) {
+        __syncwarp();
+        const int lpr = ncols >> 3;            // lanes per row (16 B each)
+        const int rpi = 32 / lpr;              // rows per instruction
+        const int cc = lane % lpr;
+#pragma unroll 1
+        for (int it = 0; it < lpr; ++it) {     // 32 rows / rpi == lpr iterations
+          const int rr = it * rpi + lane / lpr;
+          const int64_t grow = row0 + rr;
+          const int64_t col = ocol0 + cc * 8;
+          if (grow < p.M && col < n_out) {
+            uint4 q = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+            const int64_t orow = perm_row(grow, p.perm_a, p.perm_b);
+            if (p.R1 || p.R2) {
+              __half2* h = reinterpret_cast<__half2*>(&q);
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(h[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; }
+              if (p.R1) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.R1 + grow * p.ldr1 + col));
+                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ha[t]); v[2 * t] += p.r1_scale * f.x; v[2 * t + 1] += p.r1_scale * f.y; }
+              }
+              if (p.R2) {
+                const uint4 a = *reinterpret_cast<const uint4*>(p.R2 + orow * p.ldr2 + col);
+                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ha[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
+              }
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + orow * p.ldc + col) = q;
+          }
+        }
+        __syncwarp();
+      };
+      // fp32 values of 32 accumulator columns -> + bias + rowbias, * scale
+      auto finish32 = [&](const uint32_t* r, float* v, int64_t col0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (col0 + 32 <= p.N) {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (p.rowbias) {
+            const float4* rb = reinterpret_cast<const float4*>(p.rowbias + rbrow * p.rb_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(rb + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+        } else {
+          for (int i = 0; i < 32; ++i) {
+            if (col0 + i < p.N) {
+              if (p.bias) v[i] += __ldg(p.bias + col0 + i);
+              if (p.rowbias) v[i] += __ldg(p.rowbias + rbrow * p.rb_ld + col0 + i);
+            }
+          }
+        }
+        if (p.acc_scale != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
+        }
+      };
+      // stage 32 fp32 values as fp16 into this thread's row of the staging tile at 16-byte chunk offset `c0`
+      auto stage32 = [&](const float* v, int c0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 q;
+          uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) w[t] = pack_f16x2(v[c * 8 + 2 * t], v[c * 8 + 2 * t + 1]);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + (((c0 + c) ^ (lane & 7)) << 4)) = q;
+        }
+      };
+
+      if (p.out_f32) {
+        // fp32 output (time-embedding table only): direct per-row stores
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           uint32_t r[32];
@@ -173,113 +267,55 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           const int64_t col0 = (int64_t)nt * BN + ch * 32;
           if (row_ok && col0 < p.N) {
             float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            const bool full = col0 + 32 <= p.N;
-            if (p.bias) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
-            }
-            if (p.rowbias) {
-              const float* rb = p.rowbias + rbrow * p.rb_ld + col0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (full || col0 + i < p.N) v[i] += __ldg(rb + i);
-            }
-            if (p.acc_scale != 1.0f) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
-            }
-            if (p.R1) {
-              const __half* r1 = p.R1 + row * p.ldr1 + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint4 q = __ldg(reinterpret_cast<const uint4*>(r1) + i);
-                  const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(h[j]);
-                    v[i * 8 + 2 * j] += p.r1_scale * f.x;
-                    v[i * 8 + 2 * j + 1] += p.r1_scale * f.y;
-                  }
-                }
-              } else {
-                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) v[i] += p.r1_scale * __half2float(r1[i]);
-              }
-            }
-            if (p.R2) {
-              const __half* r2 = p.R2 + orow * p.ldr2 + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint4 q = __ldg(reinterpret_cast<const uint4*>(r2) + i);
-                  const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(h[j]);
-                    v[i * 8 + 2 * j] += f.x;
-                    v[i * 8 + 2 * j + 1] += f.y;
-                  }
-                }
-              } else {
-                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) v[i] += __half2float(r2[i]);
-              }
-            }
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.C) + orow * p.ldc + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              } else {
-                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = v[i];
-              }
-            } else {
-              __half* o = reinterpret_cast<__half*>(p.C) + orow * p.ldc + col0;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  uint4 q;
-                  __half2* h = reinterpret_cast<__half2*>(&q);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i * 8 + 2 * j], v[i * 8 + 2 * j + 1]);
-                  reinterpret_cast<uint4*>(o)[i] = q;
-                }
-              } else {
-                for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = __float2half_rn(v[i]);
-              }
-            }
+            finish32(r, v, col0);
+            float* o = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
+            for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = v[i];
           }
         }
-      } else {
-        // GEGLU: column blocks come as (u[32] | g[32]); bias only
+      } else if (!p.geglu) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 64; ++ch) {
-          uint32_t ru[32], rg[32];
-          tmem_ld32(taddr + ch * 64, ru);
-          tmem_ld32(taddr + ch * 64 + 32, rg);
-          tmem_wait_ld();
-          const int64_t col0 = (int64_t)nt * BN + ch * 64;
-          if (row_ok && col0 < p.N) {
-            __half* o = reinterpret_cast<__half*>(p.C) + orow * p.ldc + col0 / 2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 q;
-              __half2* h = reinterpret_cast<__half2*>(&q);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int e = i * 8 + 2 * j;
-                float u0 = __uint_as_float(ru[e]), u1 = __uint_as_float(ru[e + 1]);
-                float g0 = __uint_as_float(rg[e]), g1 = __uint_as_float(rg[e + 1]);
-                if (p.bias) {
-                  u0 += __ldg(p.bias + col0 + e); u1 += __ldg(p.bias + col0 + e + 1);
-                  g0 += __ldg(p.bias + col0 + 32 + e); g1 += __ldg(p.bias + col0 + 32 + e + 1);
-                }
-                h[j] = __floats2half2_rn(u0 * gelu_erf(g0), u1 * gelu_erf(g1));
-              }
-              reinterpret_cast<uint4*>(o)[i] = q;
-            }
+        for (int cb = 0; cb < BN; cb += 64) {
+          const int w = (BN - cb) >= 64 ? 64 : 32;
+          const int64_t col0 = (int64_t)nt * BN + cb;
+          if (col0 >= p.N) break;
+          {
+            uint32_t r[32];
+            float v[32];
+            tmem_ld32(taddr + cb, r);
+            tmem_wait_ld();
+            finish32(r, v, col0);
+            stage32(v, 0);
           }
+          if (w == 64) {
+            uint32_t r[32];
+            float v[32];
+            tmem_ld32(taddr + cb + 32, r);
+            tmem_wait_ld();
+            finish32(r, v, col0 + 32);
+            stage32(v, 4);
+          }
+          flush(w, col0);
+        }
+      } else {
+        // GEGLU: accumulator columns come as (u[32] | g[32]) blocks; 128 accumulator columns -> 64 outputs
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 128) {
+          const int64_t col0 = (int64_t)nt * BN + cb;
+          if (col0 >= p.N) break;
+#pragma unroll 1
+          for (int hb = 0; hb < 2; ++hb) {
+            uint32_t ru[32], rg[32];
+            tmem_ld32(taddr + cb + hb * 64, ru);
+            tmem_ld32(taddr + cb + hb * 64 + 32, rg);
+            tmem_wait_ld();
+            float u[32], g[32];
+            finish32(ru, u, col0 + hb * 64);
+            finish32(rg, g, col0 + hb * 64 + 32);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] *= gelu_erf(g[i]);
+            stage32(u, hb * 4);
+          }
+          flush(64, col0 / 2);
         }
       }
       tc_fence_before();
@@ -377,8 +413,10 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   d.R2 = reinterpret_cast<const __half*>(a->R2); d.ldr2 = a->ldr2;
   d.C = a->C; d.ldc = a->ldc; d.geglu = a->geglu; d.out_f32 = a->out_f32;
   d.perm_a = a->perm_a; d.perm_b = a->perm_b;
-  if (a->geglu && (a->rowbias || a->R1 || a->R2 || a->out_f32 || a->perm_a || (a->N % 64)))
-    return fail(A3D_EINVAL, "a3d_gemm: GEGLU epilogue supports bias only and needs N %% 64 == 0");
+  if (a->geglu && (a->out_f32 || (a->N % 128)))
+    return fail(A3D_EINVAL, "a3d_gemm: GEGLU epilogue needs fp16 output and N %% 128 == 0");
+  if (a->out_f32 && (a->R1 || a->R2 || a->perm_a))
+    return fail(A3D_EINVAL, "a3d_gemm: fp32 output supports bias / row-bias only");
 
   SimtConv cv{0, 0, 0, 0, 1, 0, 0};
   if (a->a_mode == A3D_A_CONV3) {
@@ -394,7 +432,7 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   }
 
   // ---- can the tensor-core path take it?
-  bool tc_ok = (a->K % kBK == 0) && ((reinterpret_cast<uintptr_t>(a->A) & 15) == 0) &&
+  bool tc_ok = (a->K % kBK == 0) && (a->N % (a->geglu ? 16 : 8) == 0) && ((reinterpret_cast<uintptr_t>(a->A) & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(a->B) & 15) == 0) && (a->ldc % 8 == 0) &&
                ((reinterpret_cast<uintptr_t>(a->C) & 15) == 0);
   if (a->a_mode == A3D_A_PLAIN) tc_ok = tc_ok && (a->lda % 8 == 0) && a->lda >= a->K;
