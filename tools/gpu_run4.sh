@@ -1,0 +1,24 @@
+#!/bin/bash
+mkdir -p gpurun_out
+LOG=gpurun_out/run4.log
+: > $LOG
+run() {
+  echo "=== $1" >> $LOG
+  timeout 600 python -m pytest $2 -q -m gpu --tb=short -p no:cacheprovider -k "$1" 2>&1 | tail -n 30 >> $LOG
+}
+run "test_gemm and tc" tests/test_kernels_gpu.py
+run "test_conv3x3 and tc" tests/test_kernels_gpu.py
+run "test_cross_view_attention and tc" tests/test_kernels_gpu.py
+run "test_cross_attention_text_keys and tc" tests/test_kernels_gpu.py
+run "test_group_norm or test_layer_norm or test_temporal" tests/test_kernels_gpu.py
+run "indices" tests/test_raster_gpu.py
+echo "=== kernel bench" >> $LOG
+timeout 300 python tools/kernel_bench.py all >> $LOG 2>&1
+echo "=== kernel bench attention v2" >> $LOG
+A3D_ATTN_VARIANT=2 timeout 300 python tools/kernel_bench.py attn >> $LOG 2>&1
+echo "=== unet parity" >> $LOG
+timeout 900 python -m pytest tests/test_unet_gpu.py -q -m gpu --tb=short -p no:cacheprovider -s 2>&1 | tail -n 20 >> $LOG
+echo "=== bench" >> $LOG
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01b.json 2>> $LOG
+cat gpurun_out/bench_r01b.json >> $LOG
+tail -n 150 $LOG
