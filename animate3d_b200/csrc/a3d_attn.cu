@@ -633,7 +633,8 @@ struct Attn3Cfg {
   static constexpr int kSmemQ = 2 * kQBox;
   static constexpr int kSmemK = kStages * kKVBox;
   static constexpr int kSmemV = kStages * kKVBox;
-  static constexpr int kSmemP = 2 * kKVBox * 2;   // per group: 128 rows x 64 keys fp16 = 16 KB
+  static constexpr int kPBox = 128 * 128;          // 128 rows x 64 keys fp16 = 16 KB
+  static constexpr int kSmemP = 2 * 2 * kPBox;     // [2 groups][2 buffers]
   static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + 1024 + 512;
 };
 
@@ -648,7 +649,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kSmemQ;
   uint8_t* sV = sK + Cfg::kSmemK;
-  uint8_t* sP = sV + Cfg::kSmemV;              // [2 groups] 128 x 64 fp16, K-major, one 128B-swizzled box each
+  uint8_t* sP = sV + Cfg::kSmemV;              // [2 groups][2 buffers] 128 x 64 fp16, K-major, 128B-swizzled
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kSmemP);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;                 // [S]
@@ -657,8 +658,8 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   uint64_t* v_empty = k_empty + S;             // [S]
   uint64_t* s_full = v_empty + S;              // [2 groups][2 buffers]
   uint64_t* p_full = s_full + 4;               // [2]
-  uint64_t* pv_done = p_full + 2;              // [2]
-  uint64_t* o_full = pv_done + 2;
+  uint64_t* pv_done = p_full + 2;              // [2 groups][2 buffers]
+  uint64_t* o_full = pv_done + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -687,10 +688,8 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&p_full[g], 4);
-      mbar_init(&pv_done[g], 1);
-    }
+    for (int g = 0; g < 2; ++g) mbar_init(&p_full[g], 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&pv_done[i], 1);
     mbar_init(o_full, 1);
     mbar_fence_init();
   }
@@ -750,11 +749,11 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         const int st = j % S;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + g * Cfg::kKVBox * 2) + kk * 32, 16, 1024);
+          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + (2 * g + (j & 1)) * Cfg::kPBox) + kk * 32, 16, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + st * Cfg::kKVBox) + kk * 2048, Cfg::kKVBox, 1024);
           umma_f16(tmem_base + 256 + g * 64, adesc, bdesc, idesc_pv, (j | kk) ? 1u : 0u);
         }
-        umma_commit(&pv_done[g]);
+        umma_commit(&pv_done[2 * g + (j & 1)]);
       };
       const int ng = has1 ? 2 : 1;
       mbar_wait(q_full, 0);
@@ -786,7 +785,6 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       const int r = quad * 32 + lane;
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
       const uint32_t tmem_O = tmem_base + 256 + g * 64;
-      uint8_t* sPg = sP + g * Cfg::kKVBox * 2;
       float m_run = -INFINITY;
       const int rows_tile = p.k_box1 * p.k_box2;                  // keys a full tile holds (<= 64)
       const int keys_total = rows_tile * (n - 1) + p.rows_k;      // rows_k = valid keys of the LAST tile
@@ -809,13 +807,12 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           for (int i = 0; i < 64; ++i) if (i < valid) mx0 = fmaxf(mx0, __uint_as_float(s[i]));
         }
         const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
-        if (j > 0) {
-          mbar_wait(&pv_done[g], (j - 1) & 1);     // P_g free, O_g stable
-          tc_fence_after();
-        }
         if (j == 0) {
           m_run = m_new;
         } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
+          // rare: O_g must be stable -> the PV product of the previous step has to be complete
+          mbar_wait(&pv_done[2 * g + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          tc_fence_after();
           const float alpha = ex2_approx(m_run - m_new);
 #pragma unroll 1
           for (int c = 0; c < Cfg::kDv / 16; ++c) {
@@ -830,6 +827,8 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           m_run = m_new;
         }
         const float neg_m = -m_run;
+        uint8_t* sPg = sP + (2 * g + (j & 1)) * Cfg::kPBox;
+        if (j >= 2) mbar_wait(&pv_done[2 * g + (j & 1)], ((j - 2) >> 1) & 1);   // P buffer of step j-2 consumed (long ago)
 #pragma unroll
         for (int c16 = 0; c16 < 8; ++c16) {
           uint4 q;

@@ -67,7 +67,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStageOut = 8 * 4096;   // per-epilogue-warp 32 x 128 B staging tile
+  static constexpr int kStageOut = 0;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -168,13 +168,12 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps: 2 per TMEM lane quadrant)
-    // TMEM -> registers (one accumulator row per thread) -> bias / row-bias / scale in fp32 -> fp16 -> per-warp swizzled
-    // staging tile in shared memory -> coalesced phase: 8 (or 4) lanes cover one 128 B (64 B) row segment; residual
-    // tiles are fetched with all loads of a flush in flight, and the result is written as full lines.
-    // The two warps of a quadrant split the tile's columns in units of 32.
+    // TMEM -> registers (one accumulator row per thread) -> bias / row-bias / scale / residuals in fp32 -> fp16 ->
+    // 256-bit global stores: every store instruction writes whole 32-byte sectors (the first version's 16-byte slivers
+    // of 32 different lines ran the output at < 0.7 TB/s).  Residual tiles are fetched with 256-bit loads issued before
+    // the TMEM wait.  The two warps of a quadrant split the tile's columns in units of 32.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* stg = smem_stage + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -188,54 +187,6 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const int64_t n_out = p.geglu ? p.N / 2 : p.N;
 
-      auto flush = [&](auto wtag, int64_t ocol0) {
-        constexpr int W = decltype(wtag)::value;   // 32 or 64 staged fp16 columns
-        constexpr int LPR = W / 8;                 // lanes per row (16 B each) == number of row groups
-        constexpr int RPI = 32 / LPR;              // rows per instruction
-        __syncwarp();
-        const int cc = lane % LPR;
-        const int64_t col = ocol0 + cc * 8;
-        const bool col_ok = col < n_out;
-#pragma unroll
-        for (int b0 = 0; b0 < LPR; b0 += 4) {
-          uint4 r1v[4], r2v[4];
-          int64_t orows[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int64_t grow = row0 + (b0 + k) * RPI + lane / LPR;
-            const bool ok = col_ok && grow < p.M;
-            orows[k] = ok ? perm_row(grow, p.perm_a, p.perm_b) : -1;
-            if (p.R1 && ok) r1v[k] = __ldg(reinterpret_cast<const uint4*>(p.R1 + grow * p.ldr1 + col));
-            if (p.R2 && ok) r2v[k] = *reinterpret_cast<const uint4*>(p.R2 + orows[k] * p.ldr2 + col);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (orows[k] < 0) continue;
-            const int rr = (b0 + k) * RPI + lane / LPR;
-            uint4 q = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-            if (p.R1 || p.R2) {
-              __half2* h = reinterpret_cast<__half2*>(&q);
-              float v[8];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(h[t]); v[2 * t] = f.x; v[2 * t + 1] = f.y; }
-              if (p.R1) {
-                const __half2* ha = reinterpret_cast<const __half2*>(&r1v[k]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ha[t]); v[2 * t] += p.r1_scale * f.x; v[2 * t + 1] += p.r1_scale * f.y; }
-              }
-              if (p.R2) {
-                const __half2* ha = reinterpret_cast<const __half2*>(&r2v[k]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { const float2 f = __half22float2(ha[t]); v[2 * t] += f.x; v[2 * t + 1] += f.y; }
-              }
-#pragma unroll
-              for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-            }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + orows[k] * p.ldc + col) = q;
-          }
-        }
-        __syncwarp();
-      };
       // fp32 values of 32 accumulator columns -> + bias + rowbias, * scale
       auto finish32 = [&](uint32_t* r, int64_t col0) {
         float* v = reinterpret_cast<float*>(r);
@@ -268,21 +219,50 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
         }
       };
-      // stage 32 fp32 values as fp16 into this thread's row of the staging tile at 16-byte chunk offset `c0`
-      auto stage32 = [&](const uint32_t* r, int c0) {
-        const float* v = reinterpret_cast<const float*>(r);
+      const int64_t orow = row_ok ? perm_row(row, p.perm_a, p.perm_b) : 0;
+      // 32 finished fp32 values of this thread's row -> (+ residuals) -> fp16 -> two 256-bit stores (two full sectors)
+      auto store32 = [&](uint32_t* r, const uint32_t* r1, const uint32_t* r2, int64_t ocol) {
+        float* v = reinterpret_cast<float*>(r);
+        if (p.R1) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 q;
-          uint32_t* w = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) w[t] = pack_f16x2(v[c * 8 + 2 * t], v[c * 8 + 2 * t + 1]);
-          *reinterpret_cast<uint4*>(stg + lane * 128 + (((c0 + c) ^ (lane & 7)) << 4)) = q;
+          for (int i = 0; i < 16; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r1[i]));
+            v[2 * i] += p.r1_scale * f.x; v[2 * i + 1] += p.r1_scale * f.y;
+          }
         }
+        if (p.R2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r2[i]));
+            v[2 * i] += f.x; v[2 * i + 1] += f.y;
+          }
+        }
+        uint32_t h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+        __half* o = reinterpret_cast<__half*>(p.C) + orow * p.ldc + ocol;
+        if (ocol + 32 <= n_out) {
+          st_global_256(o, h);
+          st_global_256(o + 16, h + 8);
+        } else {
+          for (int i = 0; i < 32; ++i) if (ocol + i < n_out) o[i] = reinterpret_cast<const __half*>(h)[i];
+        }
+      };
+      auto load_res = [&](uint32_t* r1, uint32_t* r2, int64_t ocol) {
+        if (ocol + 32 > n_out) {   // ragged tail: scalar fill
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = ocol + i < n_out;
+            if (p.R1) reinterpret_cast<__half*>(r1)[i] = ok ? p.R1[row * p.ldr1 + ocol + i] : __float2half(0.f);
+            if (p.R2) reinterpret_cast<__half*>(r2)[i] = ok ? p.R2[orow * p.ldr2 + ocol + i] : __float2half(0.f);
+          }
+          return;
+        }
+        if (p.R1) { ld_global_256(p.R1 + row * p.ldr1 + ocol, r1); ld_global_256(p.R1 + row * p.ldr1 + ocol + 16, r1 + 8); }
+        if (p.R2) { ld_global_256(p.R2 + orow * p.ldr2 + ocol, r2); ld_global_256(p.R2 + orow * p.ldr2 + ocol + 16, r2 + 8); }
       };
 
       if (p.out_f32) {
-        // fp32 output (time-embedding table only): direct per-row stores
+        // fp32 output (time-embedding table only)
         constexpr int U = BN / 32;
         const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
 #pragma unroll 1
@@ -301,26 +281,16 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         constexpr int U = BN / 32;                                  // 32-column units: 8 / 5 / 4
         const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
 #pragma unroll 1
-        for (int u = u0; u < u1; u += 2) {
+        for (int u = u0; u < u1; ++u) {
           const int64_t col0 = (int64_t)nt * BN + u * 32;
           if (col0 >= p.N) break;
-          const bool two = u + 1 < u1;
-          {
-            uint32_t r[32];
-            tmem_ld32(taddr + u * 32, r);
-            tmem_wait_ld();
+          uint32_t r[32], r1[16], r2[16];
+          tmem_ld32(taddr + u * 32, r);
+          if (row_ok) load_res(r1, r2, col0);
+          tmem_wait_ld();
+          if (row_ok) {
             finish32(r, col0);
-            stage32(r, 0);
-          }
-          if (two) {
-            uint32_t r[32];
-            tmem_ld32(taddr + u * 32 + 32, r);
-            tmem_wait_ld();
-            finish32(r, col0 + 32);
-            stage32(r, 4);
-            flush(std::integral_constant<int, 64>{}, col0);
-          } else {
-            flush(std::integral_constant<int, 32>{}, col0);
+            store32(r, r1, r2, col0);
           }
         }
       } else {
@@ -328,24 +298,21 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         constexpr int UG = BN / 64;                                 // 4 or 2 blocks per tile
         const int b0 = half ? UG / 2 : 0, b1 = half ? UG : UG / 2;
 #pragma unroll 1
-        for (int b = b0; b < b1; b += 2) {
+        for (int b = b0; b < b1; ++b) {
           const int64_t col0 = (int64_t)nt * BN + b * 64;
           if (col0 >= p.N) break;
-          const bool two = b + 1 < b1;
-#pragma unroll 1
-          for (int hb = 0; hb < (two ? 2 : 1); ++hb) {
-            uint32_t ru[32], rg[32];
-            tmem_ld32(taddr + (b + hb) * 64, ru);
-            tmem_ld32(taddr + (b + hb) * 64 + 32, rg);
-            tmem_wait_ld();
-            finish32(ru, col0 + hb * 64);
-            finish32(rg, col0 + hb * 64 + 32);
+          uint32_t ru[32], rg[32], r1[16], r2[16];
+          tmem_ld32(taddr + b * 64, ru);
+          tmem_ld32(taddr + b * 64 + 32, rg);
+          if (row_ok) load_res(r1, r2, col0 / 2);
+          tmem_wait_ld();
+          if (row_ok) {
+            finish32(ru, col0);
+            finish32(rg, col0 + 32);
 #pragma unroll
             for (int i = 0; i < 32; ++i) ru[i] = __float_as_uint(__uint_as_float(ru[i]) * gelu_erf(__uint_as_float(rg[i])));
-            stage32(ru, hb * 4);
+            store32(ru, r1, r2, col0 / 2);
           }
-          if (two) flush(std::integral_constant<int, 64>{}, col0 / 2);
-          else flush(std::integral_constant<int, 32>{}, col0 / 2);
         }
       }
       tc_fence_before();
@@ -463,8 +430,8 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
 
   // ---- can the tensor-core path take it?
   bool tc_ok = (a->K % kBK == 0) && (a->N % (a->geglu ? 16 : 8) == 0) && ((reinterpret_cast<uintptr_t>(a->A) & 15) == 0) &&
-               ((reinterpret_cast<uintptr_t>(a->B) & 15) == 0) && (a->ldc % 8 == 0) &&
-               ((reinterpret_cast<uintptr_t>(a->C) & 15) == 0);
+               ((reinterpret_cast<uintptr_t>(a->B) & 15) == 0) && (a->ldc % 16 == 0) &&
+               ((reinterpret_cast<uintptr_t>(a->C) & 31) == 0);
   if (a->a_mode == A3D_A_PLAIN) tc_ok = tc_ok && (a->lda % 8 == 0) && a->lda >= a->K;
   int boh = 0, bimg = 1, tpi = 0;
   if (a->a_mode == A3D_A_CONV3) {
@@ -479,8 +446,8 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
     }
     tc_ok = tc_ok && cv.ow * cv.s <= 256 && boh * cv.s <= 256;
   }
-  if (a->R1) tc_ok = tc_ok && (a->ldr1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a->R1) & 15) == 0);
-  if (a->R2) tc_ok = tc_ok && (a->ldr2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a->R2) & 15) == 0);
+  if (a->R1) tc_ok = tc_ok && (a->ldr1 % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->R1) & 31) == 0);
+  if (a->R2) tc_ok = tc_ok && (a->ldr2 % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->R2) & 31) == 0);
   int impl = a->impl;
   if (impl == A3D_GEMM_AUTO) impl = tc_ok ? A3D_GEMM_TCGEN05 : A3D_GEMM_SIMT;
   if (impl == A3D_GEMM_TCGEN05 && !tc_ok)
