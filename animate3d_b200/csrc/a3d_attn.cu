@@ -639,7 +639,7 @@ struct Attn3Cfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV) {
   using Cfg = Attn3Cfg<D>;
@@ -657,10 +657,11 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   uint64_t* k_empty = v_full + S;              // [S]
   uint64_t* v_empty = k_empty + S;             // [S]
   uint64_t* s_full = v_empty + S;              // [2 groups][2 buffers]
-  uint64_t* p_full = s_full + 4;               // [2]
-  uint64_t* pv_done = p_full + 2;              // [2 groups][2 buffers]
-  uint64_t* o_full = pv_done + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* p_full = s_full + 4;               // [2 groups][2 buffers]: a softmax group may run two steps ahead of
+                                               // the MMA thread's poll, a single parity barrier would alias
+  uint64_t* pv_done = p_full + 4;              // [2 groups][2 buffers]
+  uint64_t* o_full = pv_done + 4;              // [2 groups]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -684,16 +685,17 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     for (int i = 0; i < S; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&k_empty[i], has1 ? 2 : 1);   // one commit per MMA-issuing warp
+      mbar_init(&v_empty[i], has1 ? 2 : 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int g = 0; g < 2; ++g) mbar_init(&p_full[g], 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
     for (int i = 0; i < 4; ++i) mbar_init(&pv_done[i], 1);
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 3) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -731,11 +733,14 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         load_v(j);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // one MMA-issuing warp per query tile: the wait -> issue -> commit chain of a single thread (~500 cycles per
+    // tile-step) would otherwise serialise both tiles
+    const int g = warp - 1;
+    if (lane == 0 && (g == 0 || has1)) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
-      auto issue_qk = [&](int g, int j) {      // S[g][j&1] = Q_g K_j^T
+      auto issue_qk = [&](int j) {      // S[g][j&1] = Q_g K_j^T
         const int st = j % S;
 #pragma unroll
         for (int kk = 0; kk < Cfg::kDqk / 16; ++kk) {
@@ -745,7 +750,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         }
         umma_commit(&s_full[2 * g + (j & 1)]);
       };
-      auto issue_pv = [&](int g, int j) {      // O_g += P_g(j) V_j
+      auto issue_pv = [&](int j) {      // O_g += P_g(j) V_j
         const int st = j % S;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -755,31 +760,31 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         }
         umma_commit(&pv_done[2 * g + (j & 1)]);
       };
-      const int ng = has1 ? 2 : 1;
       mbar_wait(q_full, 0);
       for (int j0 = 0; j0 < 2 && j0 < n; ++j0) {
         mbar_wait(&k_full[j0 % S], (j0 / S) & 1);
         tc_fence_after();
-        for (int g = 0; g < ng; ++g) issue_qk(g, j0);
+        issue_qk(j0);
       }
       for (int j = 0; j < n; ++j) {
         const bool ahead = j + 2 < n;
+        mbar_wait(&p_full[2 * g + (j & 1)], (j >> 1) & 1);
         mbar_wait(&v_full[j % S], (j / S) & 1);
-        if (ahead) mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
-        for (int g = 0; g < ng; ++g) {
-          mbar_wait(&p_full[g], j & 1);
+        tc_fence_after();
+        issue_pv(j);
+        if (ahead) {
+          mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
           tc_fence_after();
-          issue_pv(g, j);
-          if (ahead) issue_qk(g, j + 2);
+          issue_qk(j + 2);
         }
+        // every MMA this warp issued so far (QK^T of steps <= j+2, PV of steps <= j) precedes these commits
         umma_commit(&v_empty[j % S]);
-        // the QK^T of steps j and j+1 were issued earlier and every MMA issued so far precedes this commit:
         umma_commit(&k_empty[j % S]);
       }
-      umma_commit(o_full);
+      umma_commit(&o_full[g]);
     }
-  } else {
-    const int g = (warp - 2) >> 2;
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2;
     if (g == 0 || has1) {
       const int quad = warp & 3;
       const int r = quad * 32 + lane;
@@ -829,31 +834,42 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         const float neg_m = -m_run;
         uint8_t* sPg = sP + (2 * g + (j & 1)) * Cfg::kPBox;
         if (j >= 2) mbar_wait(&pv_done[2 * g + (j & 1)], ((j - 2) >> 1) & 1);   // P buffer of step j-2 consumed (long ago)
+        if (valid == 64) {
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          uint4 q;
-          uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+          for (int c16 = 0; c16 < 8; ++c16) {
+            uint4 q;
+            uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int i = c16 * 8 + 2 * t;
-            float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m));
-            float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m));
-            if (valid != 64) {
-              if (i >= valid) p0 = 0.f;
-              if (i + 1 >= valid) p1 = 0.f;
+            for (int t = 0; t < 4; ++t) {
+              const int i = c16 * 8 + 2 * t;
+              qw[t] = pack_f16x2(ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)),
+                                 ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)));
             }
-            qw[t] = pack_f16x2(p0, p1);
+            *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
           }
-          *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
+        } else {   // ragged last tile: separate (rare) path so the common one carries no per-element selects
+#pragma unroll 1
+          for (int c16 = 0; c16 < 8; ++c16) {
+            uint4 q;
+            uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = c16 * 8 + 2 * t;
+              const float p0 = i < valid ? ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)) : 0.f;
+              const float p1 = i + 1 < valid ? ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)) : 0.f;
+              qw[t] = pack_f16x2(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
+        if (lane == 0) mbar_arrive(&p_full[2 * g + (j & 1)]);
       }
       (void)keys_total;
       // ---- epilogue
-      mbar_wait(o_full, 0);
+      mbar_wait(&o_full[g], 0);
       tc_fence_after();
       float inv;
       {
@@ -903,7 +919,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 3) tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1039,7 +1055,7 @@ static int launch_attn3(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
     attr_set = true;
   }
   grid.x = (grid.x + 1) / 2;
-  attn3_tc_kernel<D><<<grid, 320, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  attn3_tc_kernel<D><<<grid, 384, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }

@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference's 4D gaussian geometry for the hot path: `Gaussian4DModel.interpolate_ms_features`,
+`get_xyz`, `get_scaling`, `get_rotation` (custom/threestudio-animate3d/geometry/gaussian_4d.py:450-548) evaluated for ALL
+frames of a batch in one CUDA launch (forward and backward in liba3d.so), de-duplicated across the views of a frame.
+
+State (same tensors the reference keeps): static `_xyz [P,3]`, `_scaling [P,3]` (log), `_rotation [P,4]`, `_opacity`,
+`_features_dc`; learnable k-planes `grids[scale][plane] : [1, 16, H, W]` (gaussian_4d.py:101-117, 151-174) and the three
+bias-free MLPs delta_xyz / delta_rot / delta_scaling (119-147; VanillaMLP, threestudio/models/networks.py:214-251).
+The optional global rotation/translation branch (`use_global_trans`, 129-142, 499-511, 525-539) is not implemented yet."""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+class DeformArgs(C.Structure):
+    _fields_ = [("P", C.c_int), ("T", C.c_int), ("xyz", C.c_void_p), ("scaling", C.c_void_p), ("rotation", C.c_void_p),
+                ("times", C.c_void_p), ("num_scales", C.c_int), ("channels", C.c_int), ("hidden", C.c_int),
+                ("planes", C.c_void_p * 12), ("plane_h", C.c_int * 12), ("plane_w", C.c_int * 12),
+                ("w1", C.c_void_p * 3), ("w2", C.c_void_p * 3), ("deform_scale", C.c_int),
+                ("grad_planes", C.c_void_p * 12), ("grad_w1", C.c_void_p * 3), ("grad_w2", C.c_void_p * 3)]
+
+
+def _args(xyz, scaling, rotation, times, planes, w1s, w2s, deform_scale, gplanes=None, gw1=None, gw2=None):
+    a = DeformArgs()
+    a.P, a.T = xyz.shape[0], times.shape[0]
+    a.xyz, a.scaling, a.rotation, a.times = xyz.data_ptr(), scaling.data_ptr(), rotation.data_ptr(), times.data_ptr()
+    a.num_scales, a.channels, a.hidden = len(planes) // 6, planes[0].shape[-3], w1s[0].shape[0]
+    for i, pl in enumerate(planes):
+        a.planes[i] = pl.data_ptr()
+        a.plane_h[i], a.plane_w[i] = pl.shape[-2], pl.shape[-1]
+        if gplanes is not None:
+            a.grad_planes[i] = gplanes[i].data_ptr()
+    for m in range(3):
+        a.w1[m], a.w2[m] = w1s[m].data_ptr(), w2s[m].data_ptr()
+        if gw1 is not None:
+            a.grad_w1[m], a.grad_w2[m] = gw1[m].data_ptr(), gw2[m].data_ptr()
+    a.deform_scale = int(deform_scale)
+    return a
+
+
+class _Deform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, scaling, rotation, times, deform_scale, n_planes, *params):
+        lib = L.load()
+        planes = [p.detach().contiguous().float() for p in params[:n_planes]]
+        w1s = [p.detach().contiguous().float() for p in params[n_planes:n_planes + 3]]
+        w2s = [p.detach().contiguous().float() for p in params[n_planes + 3:n_planes + 6]]
+        xyz, scaling, rotation, times = [t.detach().contiguous().float() for t in (xyz, scaling, rotation, times)]
+        P, T = xyz.shape[0], times.shape[0]
+        means = torch.empty(T, P, 3, device=xyz.device)
+        scales = torch.empty(T, P, 3, device=xyz.device)
+        rots = torch.empty(T, P, 4, device=xyz.device)
+        a = _args(xyz, scaling, rotation, times, planes, w1s, w2s, deform_scale)
+        L.check(lib.a3d_deform_forward(C.byref(a), C.c_void_p(means.data_ptr()), C.c_void_p(scales.data_ptr()),
+                                       C.c_void_p(rots.data_ptr()), L.stream_ptr()))
+        ctx.save_for_backward(xyz, scaling, rotation, times, *planes, *w1s, *w2s)
+        ctx.meta = (deform_scale, n_planes)
+        return means, scales, rots
+
+    @staticmethod
+    def backward(ctx, g_means, g_scales, g_rots):
+        lib = L.load()
+        deform_scale, n_planes = ctx.meta
+        xyz, scaling, rotation, times, *rest = ctx.saved_tensors
+        planes, w1s, w2s = rest[:n_planes], rest[n_planes:n_planes + 3], rest[n_planes + 3:]
+        gp = [torch.zeros_like(p) for p in planes]
+        g1 = [torch.zeros_like(w) for w in w1s]
+        g2 = [torch.zeros_like(w) for w in w2s]
+        f = lambda t: None if t is None else t.contiguous().float()
+        g_means, g_scales, g_rots = f(g_means), f(g_scales), f(g_rots)
+        a = _args(xyz, scaling, rotation, times, planes, w1s, w2s, deform_scale, gp, g1, g2)
+        L.check(lib.a3d_deform_backward(C.byref(a), C.c_void_p(L.ptr(g_means)), C.c_void_p(L.ptr(g_scales)),
+                                        C.c_void_p(L.ptr(g_rots)), L.stream_ptr()))
+        return (None, None, None, None, None, None, *gp, *g1, *g2)
+
+
+class Gaussian4DModel(torch.nn.Module):
+    """Registered in the reference as "gaussian-splatting-4d" (gaussian_4d.py:67)."""
+
+    def __init__(self, xyz, scaling, rotation, opacity, features_dc, grid_size=((50, 50, 50, 8), (100, 100, 100, 16)),
+                 n_grid_dims: int = 16, n_neurons: int = 32, seed: int = 0, device="cuda"):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        for name, t in (("_xyz", xyz), ("_scaling", scaling), ("_rotation", rotation), ("_opacity", opacity), ("_features_dc", features_dc)):
+            self.register_buffer(name, t.float().to(device))      # frozen after load_ply (gaussian_4d.py:262-297)
+        self.grids = torch.nn.ModuleList()
+        for reso in grid_size:
+            planes = torch.nn.ParameterList()
+            for comb in itertools.combinations(range(4), 2):
+                shape = [1, n_grid_dims] + [reso[cc] for cc in comb[::-1]]
+                init = torch.ones(shape) if 3 in comb else torch.rand(shape, generator=g) * 0.4 + 0.1     # 168-171
+                planes.append(torch.nn.Parameter(init.to(device)))
+            self.grids.append(planes)
+        feat = n_grid_dims * len(grid_size)
+
+        def mlp(out):   # VanillaMLP: Linear(no bias) - ReLU - Linear(no bias); last layer zero-init (145-147)
+            w1 = torch.nn.Parameter((torch.rand(n_neurons, feat, generator=g) * 2 - 1).div_(feat ** 0.5).to(device))
+            w2 = torch.nn.Parameter(torch.zeros(out, n_neurons, device=device))
+            return torch.nn.ParameterList([w1, w2])
+        self.delta_xyz_network, self.delta_rot_network, self.delta_scaling_network = mlp(3), mlp(4), mlp(3)
+        self.active_sh_degree = 0
+
+    @property
+    def get_opacity(self):
+        return torch.sigmoid(self._opacity)
+
+    def deform_all(self, timestamps: torch.Tensor, deform_scale: bool = True):
+        """(means3D [T,P,3], scales [T,P,3], rotations [T,P,4]) for every timestamp in one launch.  Frames with
+        timestamp == -1 keep the static gaussians when `first_frame_trainable` is off in the caller."""
+        planes = [p for pl in self.grids for p in pl]
+        nets = (self.delta_xyz_network, self.delta_rot_network, self.delta_scaling_network)
+        params = planes + [n[0] for n in nets] + [n[1] for n in nets]
+        return _Deform.apply(self._xyz, self._scaling, self._rotation, timestamps.float().to(self._xyz.device), deform_scale,
+                             len(planes), *params)

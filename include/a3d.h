@@ -186,6 +186,37 @@ int a3d_raster_backward(const a3d_raster_args* args, const float* dL_dcolor, con
 int a3d_raster_binning_tap(const void* workspace, int P, int H, int W, int num_cams, int64_t max_rendered, int cam,
                            uint64_t* keys_out, uint32_t* point_list_out, uint32_t* ranges_out, void* stream);
 
+/* ---------------------------------------------------------------- 4D deformation field (k-planes + MLPs) --------- */
+/* Per (frame, gaussian): 32 k-planes features (num_scales x 16 channels, product over the 6 coordinate planes of
+ * bilinear samples at (x,y,z,t)) -> three bias-free MLPs 32 -> 32 (ReLU) -> {3,4,3} -> means = xyz + d,
+ * scales = exp(scaling + d) (d only when deform_scale), rotations = normalize(rotation + d).
+ * Replaces Gaussian4DModel.interpolate_ms_features / get_xyz / get_scaling / get_rotation
+ * (custom/threestudio-animate3d/geometry/gaussian_4d.py:450-548), without the optional global rot/trans branch.
+ * planes[s*6+p] is a [channels, plane_h, plane_w] fp32 grid for coordinate pair p of (0,1),(0,2),(0,3),(1,2),(1,3),(2,3)
+ * with the FIRST coordinate of the pair indexing W (grid_sample convention).  w1[m] [hidden, num_scales*channels],
+ * w2[m] [out_m, hidden] for m = 0 (xyz, 3), 1 (rotation, 4), 2 (scaling, 3).  Outputs are [T, P, *].
+ * backward accumulates (+=) into grad_planes / grad_w1 / grad_w2 (caller zeroes them). */
+typedef struct a3d_deform_args {
+  int P, T;
+  const float* xyz;        /* [P,3] */
+  const float* scaling;    /* [P,3] raw (log) scales */
+  const float* rotation;   /* [P,4] raw quaternions */
+  const float* times;      /* [T] timestamps in [-1,1] */
+  int num_scales, channels, hidden;
+  const float* planes[12];
+  int plane_h[12], plane_w[12];
+  const float* w1[3];
+  const float* w2[3];
+  int deform_scale;
+  float* grad_planes[12];  /* backward only; entries may be NULL */
+  float* grad_w1[3];
+  float* grad_w2[3];
+} a3d_deform_args;
+
+int a3d_deform_forward(const a3d_deform_args* args, float* means, float* scales, float* rotations, void* stream);
+int a3d_deform_backward(const a3d_deform_args* args, const float* dL_dmeans, const float* dL_dscales, const float* dL_drotations,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -154,6 +154,27 @@ def load_camera_fns():
     return ns["get_camera"]
 
 
+def load_kplanes_fns():
+    """exec grid_sample_wrapper and Gaussian4DModel.interpolate_ms_features out of gaussian_4d.py (the module imports
+    threestudio / simple_knn / the un-vendored threestudio-3dgs package and cannot be imported here)."""
+    import itertools
+    from typing import Collection, Iterable, Optional
+    src = open(os.path.join(REF, "custom/threestudio-animate3d/geometry/gaussian_4d.py")).read()
+    tree = ast.parse(src)
+    fns = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "grid_sample_wrapper":
+            fns.append(node)
+        if isinstance(node, ast.ClassDef) and node.name == "Gaussian4DModel":
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == "interpolate_ms_features":
+                    fns.append(sub)
+    ns = {"torch": torch, "F": F, "nn": nn, "itertools": itertools, "Collection": Collection, "Iterable": Iterable,
+          "Optional": Optional}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "gaussian_4d_kplanes", "exec"), ns)
+    return ns["interpolate_ms_features"]
+
+
 def attn_weights(attn, prefix):
     return {f"{prefix}.to_q.weight": attn.to_q.weight.detach().clone(),
             f"{prefix}.to_k.weight": attn.to_k.weight.detach().clone(),
@@ -232,6 +253,22 @@ def main():
         m = SinePositionalEncoding2D(nfeat, normalize=True)
         emb[(nfeat, h, w)] = m._forward(torch.zeros(1, h, w))[0].clone()
     torch.save(emb, os.path.join(OUT, "ref_embeddings.pt"))
+
+    # k-planes lookup of the 4D gaussians (gaussian_4d.py:39-64, 450-484)
+    interp = load_kplanes_fns()
+    import itertools
+    g = torch.Generator().manual_seed(77)
+    grids = []
+    for reso in ([6, 5, 7, 4], [12, 10, 14, 8]):
+        planes = nn.ParameterList()
+        for comb in itertools.combinations(range(4), 2):
+            planes.append(nn.Parameter(torch.rand([1, 8] + [reso[cc] for cc in comb[::-1]], generator=g)))
+        grids.append(planes)
+    pts = torch.rand(200, 4, generator=g) * 2.4 - 1.2          # some points outside [-1,1] -> border padding
+    with torch.no_grad():
+        feats = interp(None, pts, grids)
+    torch.save({"grids": [[p.detach().clone() for p in pl] for pl in grids], "pts": pts, "feats": feats},
+               os.path.join(OUT, "ref_kplanes.pt"))
 
     get_camera = load_camera_fns()
     cam = {n: get_camera(n) for n in (1, 4, 8)}
