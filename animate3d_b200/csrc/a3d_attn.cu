@@ -677,7 +677,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == 10 && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
@@ -695,7 +695,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     mbar_init(&o_full[1], 1);
     mbar_fence_init();
   }
-  if (warp == 3) tmem_alloc<512>(tmem_slot);
+  if (warp == 11) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -703,7 +703,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   const int q_i3 = qb % p.q_e3;
   const int q_i4 = qb / p.q_e3;
 
-  if (warp == 0) {
+  if (warp == 10) {
     if (lane == 0) {
       const int kb = qb / p.kv_div;
       const int k_i3 = p.kv_i3_zero ? 0 : (kb % p.k_e3);
@@ -733,31 +733,32 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         load_v(j);
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp == 8 || warp == 9) {
     // one MMA-issuing warp per query tile: the wait -> issue -> commit chain of a single thread (~500 cycles per
     // tile-step) would otherwise serialise both tiles
-    const int g = warp - 1;
+    const int g = warp - 8;
     if (lane == 0 && (g == 0 || has1)) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
+      // descriptors differ only in the 14-bit (address >> 4) field: build the bases once, add offsets in the loop
+      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + g * Cfg::kQBox), 16, 1024);
+      const uint64_t dk = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t dv = make_smem_desc_sw128(smem_u32(sV), Cfg::kKVBox, 1024);
+      const uint64_t dp = make_smem_desc_sw128(smem_u32(sP + 2 * g * Cfg::kPBox), 16, 1024);
+      const uint32_t tS = tmem_base + 2 * g * 64, tO = tmem_base + 256 + g * 64;
       auto issue_qk = [&](int j) {      // S[g][j&1] = Q_g K_j^T
-        const int st = j % S;
+        const uint64_t kb_ = dk + (uint64_t)((j % S) * (Cfg::kKVBox >> 4));
 #pragma unroll
-        for (int kk = 0; kk < Cfg::kDqk / 16; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + g * Cfg::kQBox) + kk * 32, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + st * Cfg::kKVBox) + kk * 32, 16, 1024);
-          umma_f16(tmem_base + (2 * g + (j & 1)) * 64, adesc, bdesc, idesc_qk, kk ? 1u : 0u);
-        }
+        for (int kk = 0; kk < Cfg::kDqk / 16; ++kk)
+          umma_f16(tS + (j & 1) * 64, dq + (uint64_t)(2 * kk), kb_ + (uint64_t)(2 * kk), idesc_qk, kk ? 1u : 0u);
         umma_commit(&s_full[2 * g + (j & 1)]);
       };
       auto issue_pv = [&](int j) {      // O_g += P_g(j) V_j
-        const int st = j % S;
+        const uint64_t pb_ = dp + (uint64_t)((j & 1) * (Cfg::kPBox >> 4));
+        const uint64_t vb_ = dv + (uint64_t)((j % S) * (Cfg::kKVBox >> 4));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t adesc = make_smem_desc_sw128(smem_u32(sP + (2 * g + (j & 1)) * Cfg::kPBox) + kk * 32, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sV + st * Cfg::kKVBox) + kk * 2048, Cfg::kKVBox, 1024);
-          umma_f16(tmem_base + 256 + g * 64, adesc, bdesc, idesc_pv, (j | kk) ? 1u : 0u);
-        }
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tO, pb_ + (uint64_t)(2 * kk), vb_ + (uint64_t)(128 * kk), idesc_pv, (j | kk) ? 1u : 0u);
         umma_commit(&pv_done[2 * g + (j & 1)]);
       };
       mbar_wait(q_full, 0);
@@ -783,8 +784,8 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       }
       umma_commit(&o_full[g]);
     }
-  } else if (warp >= 4) {
-    const int g = (warp - 4) >> 2;
+  } else if (warp < 8) {
+    const int g = warp >> 2;
     if (g == 0 || has1) {
       const int quad = warp & 3;
       const int r = quad * 32 + lane;
@@ -919,7 +920,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) tmem_dealloc<512>(tmem_base);
+  if (warp == 11) tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

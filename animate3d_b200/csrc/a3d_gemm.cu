@@ -91,7 +91,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -104,14 +104,15 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 9) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer (highest warp ids: the scheduler
+    // prefers them, so the single-thread control warps are not starved by the 8 busy epilogue warps)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -137,7 +138,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(kBM, BN, false, false);
@@ -173,7 +174,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
     // of 32 different lines ran the output at < 0.7 TB/s).  Residual tiles are fetched with 256-bit loads issued before
     // the TMEM wait.  The two warps of a quadrant split the tile's columns in units of 32.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = warp >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -323,7 +324,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (warp == 9) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -93,13 +93,28 @@ class _Lin:
         self.b = None if b is None else b.to(device=device, dtype=torch.float32).contiguous()
         self.n, self.k = self.w.shape
 
+    def rows(self, a: int, b: int) -> "_Lin":
+        """Row slice [a, b) of the weight (and bias) without copying -- used to split a fused projection."""
+        o = object.__new__(_Lin)
+        o.w, o.b = self.w[a:b], None if self.b is None else self.b[a:b]
+        o.n, o.k = b - a, self.k
+        return o
+
 
 class MVUNetMotionModel:
     """Drop-in for the reference class on the inference path (eval mode, no grad -- the reference never back-propagates
     through the UNet: animatemv_guidance.py:422, pipeline.py:758)."""
 
-    def __init__(self, config: Optional[UNetConfig] = None, device: str = "cuda", **kwargs):
+    def __init__(self, config: Optional[UNetConfig] = None, device: str = "cuda", view_group=None, **kwargs):
+        """view_group: a torch.distributed process group whose ranks each hold ONE view of the same prompts (SURVEY 8e,
+        "views span ranks").  Everything stays local except the cross-view attentions, whose K/V are all-gathered over the
+        group (NCCL over NVLink); forward() is then called with the local view only and num_views=1."""
         self.cfg = config or UNetConfig(**kwargs)
+        self.view_group = view_group
+        self.view_world = 1
+        if view_group is not None:
+            import torch.distributed as dist
+            self.view_world = dist.get_world_size(view_group)
         self.config = self.cfg        # diffusers-style attribute used by the pipeline (`unet.config.in_channels`)
         self.device = torch.device(device)
         self.dtype = HALF
@@ -353,6 +368,26 @@ class MVUNetMotionModel:
         self.launches += 1
         ops.attention(q, k, v, out, ostr, heads=self.cfg.num_attention_heads, d=d, scale=d ** -0.5, impl=self.attn_impl, **kw)
 
+    def _gathered_views(self, ln, lin, n_q, M, lvl, hq, q_strides, kv_strides, hw, F, B, table, rb_div, rb_mod):
+        """View-parallel projection: the fused [q.. | k | v] projection is split by rows into a local query GEMM and a K|V
+        GEMM whose output is all-gathered over the view group; returns (q view, second q view, k view, v view)."""
+        import torch.distributed as dist
+        V = self.view_world
+        n_kv = lin.n - n_q
+        qb = self._buf(f"qkv{lvl}", (M, n_q))
+        kv_loc = self._buf(f"kvloc{lvl}", (M, n_kv))
+        kv_all = self._buf(f"kvall{lvl}", (V, M, n_kv))
+        rb = {} if table is None else {"rb_div": rb_div, "rb_mod": rb_mod}
+        self._gemm(ln, lin.rows(0, n_q), qb, M, rowbias=None if table is None else table[:, :n_q], **rb)
+        self._gemm(ln, lin.rows(n_q, lin.n), kv_loc, M, rowbias=None if table is None else table[:, n_q:], **rb)
+        dist.all_gather_into_tensor(kv_all.view(-1), kv_loc.view(-1), group=self.view_group)
+        ext_q, ext_k = (hw, 1, F, B), (hw, V, F, B)
+        vq = ops.view5(qb, 0, n_q, q_strides(n_q), ext_q)
+        vq2 = ops.view5(qb, hq, n_q - hq, q_strides(n_q), ext_q) if n_q > hq else None
+        vk = ops.view5(kv_all, 0, n_kv, kv_strides(n_kv), ext_k)
+        vv = ops.view5(kv_all, hq, n_kv - hq, kv_strides(n_kv), ext_k)
+        return vq, vq2, vk, vv
+
     def _transformer2d(self, t, x, n_img, h, w, lvl, B, Nv, F):
         """Transformer2DModel + BasicTransformerBlock with the MVDreamI2V (attn1) and IPAdapter (attn2) processors."""
         cfg = self.cfg
@@ -370,15 +405,20 @@ class MVUNetMotionModel:
         self._ln(tok, t["ln1"], ln, M, c)
         nq = t["qkv"].n
         qkv = self._buf(f"qkv{lvl}", (M, nq))
-        self._gemm(ln, t["qkv"], qkv, M)
-        st = (nq, F * hw * nq, hw * nq, Nv * F * hw * nq)           # rows ordered (b n f p)
-        ext = (hw, Nv, F, B)
-        ostr = (c, F * hw * c, hw * c, Nv * F * hw * c)
         hq = heads * dqk
-        vq = ops.view5(qkv, 0, nq, st, ext)
-        vqi = ops.view5(qkv, hq, nq - hq, st, ext)
-        vk = ops.view5(qkv, 2 * hq, nq - 2 * hq, st, ext)
-        vv = ops.view5(qkv, 3 * hq, nq - 3 * hq, st, ext)
+        ostr = (c, F * hw * c, hw * c, Nv * F * hw * c)
+        if self.view_group is None:
+            self._gemm(ln, t["qkv"], qkv, M)
+            st = (nq, F * hw * nq, hw * nq, Nv * F * hw * nq)           # rows ordered (b n f p)
+            ext = (hw, Nv, F, B)
+            vq = ops.view5(qkv, 0, nq, st, ext)
+            vqi = ops.view5(qkv, hq, nq - hq, st, ext)
+            vk = ops.view5(qkv, 2 * hq, nq - 2 * hq, st, ext)
+            vv = ops.view5(qkv, 3 * hq, nq - 3 * hq, st, ext)
+        else:
+            # views span ranks: local rows are (b f p) of ONE view; K|V of every view are all-gathered
+            vq, vqi, vk, vv = self._gathered_views(ln, t["qkv"], 2 * hq, M, lvl, hq, (lambda n_: (n_, F * hw * n_, hw * n_, F * hw * n_)),
+                                                   (lambda n_: (n_, M * n_, hw * n_, F * hw * n_)), hw, F, B, None, 0, 0)
         o1 = self._buf(f"ao{lvl}", (M, c))
         o2 = self._buf(f"ao2_{lvl}", (M, c))
         self._attn(vq, vk, vv, o1, ostr, d)
@@ -434,13 +474,17 @@ class MVUNetMotionModel:
             self._gemm(ao, p["t_out"], tmp, M)
             # spatial (cross-view) branch: (x + pos2d) W == x W + table[p]
             ns = p["s_qkv"].n
-            sq = self._buf(f"qkv{lvl}", (M, ns))
-            self._gemm(ln, p["s_qkv"], sq, M, rowbias=p["s_table"], rb_div=F, rb_mod=hw)
-            st = (F * ns, hw * F * ns, ns, Nv * hw * F * ns)            # rows ordered (b n p f)
-            ext = (hw, Nv, F, B)
-            vq = ops.view5(sq, 0, ns, st, ext)
-            vk = ops.view5(sq, hq, ns - hq, st, ext)
-            vv = ops.view5(sq, 2 * hq, ns - 2 * hq, st, ext)
+            if self.view_group is None:
+                sq = self._buf(f"qkv{lvl}", (M, ns))
+                self._gemm(ln, p["s_qkv"], sq, M, rowbias=p["s_table"], rb_div=F, rb_mod=hw)
+                st = (F * ns, hw * F * ns, ns, Nv * hw * F * ns)            # rows ordered (b n p f)
+                ext = (hw, Nv, F, B)
+                vq = ops.view5(sq, 0, ns, st, ext)
+                vk = ops.view5(sq, hq, ns - hq, st, ext)
+                vv = ops.view5(sq, 2 * hq, ns - 2 * hq, st, ext)
+            else:
+                vq, _, vk, vv = self._gathered_views(ln, p["s_qkv"], hq, M, lvl, hq, (lambda n_: (F * n_, hw * F * n_, n_, hw * F * n_)),
+                                                     (lambda n_: (F * n_, M * n_, n_, hw * F * n_)), hw, F, B, p["s_table"], F, hw)
             self._attn(vq, vk, vv, ao2, (F * c, hw * F * c, c, Nv * hw * F * c), d)
             # AlphaBlender: alpha * (to_out_sp(S)) + (1 - alpha) * T, plus the block residual, in one epilogue
             al = p["alpha"]
