@@ -30,6 +30,7 @@ struct AttnDev {
   int64_t os1, os2, os3, os4;
   int accumulate;
   float out_scale;
+  long long* trace;   // debug: per-step timestamps of CTA (0,0,0) (null in production)
 };
 
 constexpr float kRescaleLog2 = 8.0f;
@@ -770,14 +771,18 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       for (int j = 0; j < n; ++j) {
         const bool ahead = j + 2 < n;
         mbar_wait(&p_full[2 * g + (j & 1)], (j >> 1) & 1);
+        const bool tr = p.trace && g == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64;
+        if (tr) p.trace[j * 16 + 0] = clock64();
         mbar_wait(&v_full[j % S], (j / S) & 1);
         tc_fence_after();
         issue_pv(j);
+        if (tr) p.trace[j * 16 + 1] = clock64();
         if (ahead) {
           mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
           tc_fence_after();
           issue_qk(j + 2);
         }
+        if (tr) p.trace[j * 16 + 2] = clock64();
         // every MMA this warp issued so far (QK^T of steps <= j+2, PV of steps <= j) precedes these commits
         umma_commit(&v_empty[j % S]);
         umma_commit(&k_empty[j % S]);
@@ -796,11 +801,15 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       const int keys_total = rows_tile * (n - 1) + p.rows_k;      // rows_k = valid keys of the LAST tile
       for (int j = 0; j < n; ++j) {
         const int valid = (j == n - 1) ? p.rows_k : rows_tile;
+        const bool tr = p.trace && warp == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64;
+        if (tr) p.trace[j * 16 + 4] = clock64();
         mbar_wait(&s_full[2 * g + (j & 1)], (j >> 1) & 1);
+        if (tr) p.trace[j * 16 + 5] = clock64();
         tc_fence_after();
         uint32_t s[64];
         tmem_ld64(tmem_base + lane_addr + (2 * g + (j & 1)) * 64, s);
         tmem_wait_ld();
+        if (tr) p.trace[j * 16 + 6] = clock64();
         float mx0 = -INFINITY, mx1 = -INFINITY;
         if (valid == 64) {
 #pragma unroll
@@ -813,6 +822,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           for (int i = 0; i < 64; ++i) if (i < valid) mx0 = fmaxf(mx0, __uint_as_float(s[i]));
         }
         const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
+        if (tr) p.trace[j * 16 + 7] = clock64();
         if (j == 0) {
           m_run = m_new;
         } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
@@ -863,10 +873,12 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
             *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
           }
         }
+        if (tr) p.trace[j * 16 + 8] = clock64();
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[2 * g + (j & 1)]);
+        if (tr) p.trace[j * 16 + 9] = clock64();
       }
       (void)keys_total;
       // ---- epilogue
@@ -1061,6 +1073,8 @@ static int launch_attn3(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
   return A3D_OK;
 }
 
+static long long* g_attn_trace = nullptr;
+
 static int attn_variant() {
   static int v = -1;
   if (v < 0) {
@@ -1116,6 +1130,7 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   dev.os1 = a->os1; dev.os2 = a->os2; dev.os3 = a->os3; dev.os4 = a->os4;
   dev.accumulate = a->accumulate;
   dev.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
+  dev.trace = g_attn_trace;
   if ((a->os1 | a->os2 | a->os3 | a->os4) % 8 || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
   const CUtensorMap *mq, *mk, *mv;
@@ -1132,4 +1147,10 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
     case 80: return launch_attn<80>(dev, mq, mk, mv, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
   }
+}
+
+// debug hook (not part of the product path): record per-step clock64 timestamps of CTA (0,0,0) of the next v3 launches
+extern "C" int a3d_debug_set_attn_trace(void* device_buffer_1024_int64) {
+  a3d::g_attn_trace = reinterpret_cast<long long*>(device_buffer_1024_int64);
+  return A3D_OK;
 }

@@ -217,6 +217,9 @@ int a3d_deform_forward(const a3d_deform_args* args, float* means, float* scales,
 int a3d_deform_backward(const a3d_deform_args* args, const float* dL_dmeans, const float* dL_dscales, const float* dL_drotations,
                         void* stream);
 
+/* debug hook: per-step clock64 timestamps of CTA (0,0,0) of the following head-dim-40 attention launches (NULL = off) */
+int a3d_debug_set_attn_trace(void* device_buffer_1024_int64);
+
 #ifdef __cplusplus
 }
 #endif

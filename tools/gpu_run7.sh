@@ -15,3 +15,6 @@ timeout 300 python tools/kernel_bench.py all >> $LOG 2>&1
 echo "=== kernel bench attn v2" >> $LOG
 A3D_ATTN_VARIANT=2 timeout 300 python tools/kernel_bench.py attn >> $LOG 2>&1
 tail -n 60 $LOG
+echo "=== attention trace" >> $LOG
+timeout 300 python tools/attn_trace.py >> $LOG 2>&1
+tail -n 30 $LOG
