@@ -797,6 +797,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
       const uint32_t tmem_O = tmem_base + 256 + g * 64;
       float m_run = -INFINITY;
+      if (g == 1) __nanosleep(350);   // the groups run at the same period: an initial offset keeps their MUFU phases apart
       const int rows_tile = p.k_box1 * p.k_box2;                  // keys a full tile holds (<= 64)
       const int keys_total = rows_tile * (n - 1) + p.rows_k;      // rows_k = valid keys of the LAST tile
       for (int j = 0; j < n; ++j) {
@@ -810,23 +811,9 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         tmem_ld64(tmem_base + lane_addr + (2 * g + (j & 1)) * 64, s);
         tmem_wait_ld();
         if (tr) p.trace[j * 16 + 6] = clock64();
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        if (valid == 64) {
-#pragma unroll
-          for (int i = 0; i < 64; i += 4) {
-            mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-            mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) if (i < valid) mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-        }
-        const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * p.scale_log2);
-        if (tr) p.trace[j * 16 + 7] = clock64();
-        if (j == 0) {
-          m_run = m_new;
-        } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
-          // rare: O_g must be stable -> the PV product of the previous step has to be complete
+        uint8_t* sPg = sP + (2 * g + (j & 1)) * Cfg::kPBox;
+        if (j >= 2) mbar_wait(&pv_done[2 * g + (j & 1)], ((j - 2) >> 1) & 1);   // P buffer of step j-2 consumed (long ago)
+        auto rescale_o = [&](float m_new) {   // rare: O_g must be stable -> PV of the previous step has to be complete
           mbar_wait(&pv_done[2 * g + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
           tc_fence_after();
           const float alpha = ex2_approx(m_run - m_new);
@@ -840,12 +827,22 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
             tmem_st16(tmem_O + lane_addr + c * 16, o);
           }
           tmem_wait_st();
-          m_run = m_new;
-        }
-        const float neg_m = -m_run;
-        uint8_t* sPg = sP + (2 * g + (j & 1)) * Cfg::kPBox;
-        if (j >= 2) mbar_wait(&pv_done[2 * g + (j & 1)], ((j - 2) >> 1) & 1);   // P buffer of step j-2 consumed (long ago)
+        };
         if (valid == 64) {
+          // Single pass with a STALE stabiliser: P = exp2(s*c - m_run) uses the running max of the PREVIOUS steps, the max of
+          // this step is accumulated in the same loop (FMNMX3 on the ALU pipe hides under the MUFU-bound exponentials).
+          // Only when some row's new max exceeds the stabiliser by more than kRescaleLog2 (P could overflow fp16) is the
+          // step redone with the updated stabiliser -- after the first few steps that never happens.
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          if (j == 0) {   // no stabiliser yet: real max first
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+              mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            }
+            m_run = fmaxf(mx0, mx1) * p.scale_log2;
+          }
+          float neg_m = -m_run;
 #pragma unroll
           for (int c16 = 0; c16 < 8; ++c16) {
             uint4 q;
@@ -853,12 +850,44 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int i = c16 * 8 + 2 * t;
-              qw[t] = pack_f16x2(ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)),
-                                 ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)));
+              const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]);
+              if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
+              qw[t] = pack_f16x2(ex2_approx(fmaf(s0, p.scale_log2, neg_m)), ex2_approx(fmaf(s1, p.scale_log2, neg_m)));
             }
             *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
           }
-        } else {   // ragged last tile: separate (rare) path so the common one carries no per-element selects
+          const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
+          if (tr) p.trace[j * 16 + 7] = clock64();
+          if (j > 0 && __any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
+            const float m_up = fmaxf(m_run, m_new);
+            rescale_o(m_up);
+            m_run = m_up;
+            neg_m = -m_run;
+#pragma unroll 1
+            for (int c16 = 0; c16 < 8; ++c16) {
+              uint4 q;
+              uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int i = c16 * 8 + 2 * t;
+                qw[t] = pack_f16x2(ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)),
+                                   ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)));
+              }
+              *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
+            }
+          }
+        } else {   // ragged tile (rare): plain two-phase version with per-element masking
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int i = 0; i < 64; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+          const float m_new = fmaxf(m_run, mx * p.scale_log2);
+          if (j == 0) {
+            m_run = m_new;
+          } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
+            rescale_o(m_new);
+            m_run = m_new;
+          }
+          const float neg_m = -m_run;
 #pragma unroll 1
           for (int c16 = 0; c16 < 8; ++c16) {
             uint4 q;

@@ -309,7 +309,7 @@ def run_native(args, rank, world, local_rank):
                    "step_tflop": sf / 1e12, "achieved_tflops_per_gpu": sf / 1e12 / (ms_step * 1e-3),
                    "l2": "working set (3.1 GB fp16 weights + activations) >> 126 MB L2; no flush needed",
                    "cuda_graph": bool(model.use_cuda_graph)},
-        "roofline": {"bound": "tensor", "kernel": "attn_tc_kernel<40> (fused cross-view attention, L=4096, d=40)",
+        "roofline": {"bound": "tensor", "kernel": "a3d_attention head_dim 40 (fused cross-view attention, L=4096, 32 batches x 8 heads)",
                      "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf, "traffic": traffic,
                      "ms_per_launch": att_ms, "flop_per_launch": att_flops, "peak_source": peak_src},
         "cpu_baseline": cpu,
