@@ -797,7 +797,8 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
       const uint32_t tmem_O = tmem_base + 256 + g * 64;
       float m_run = -INFINITY;
-      if (g == 1) __nanosleep(350);   // the groups run at the same period: an initial offset keeps their MUFU phases apart
+      const bool pingpong = has1;       // both groups present -> alternate their MUFU phases
+      if (pingpong && g == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // group 0 owns the first turn
       const int rows_tile = p.k_box1 * p.k_box2;                  // keys a full tile holds (<= 64)
       const int keys_total = rows_tile * (n - 1) + p.rows_k;      // rows_k = valid keys of the LAST tile
       for (int j = 0; j < n; ++j) {
@@ -842,7 +843,10 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
             }
             m_run = fmaxf(mx0, mx1) * p.scale_log2;
           }
-          float neg_m = -m_run;
+          float neg_m = -(m_run + kPackBias);
+          // ping-pong: only one group at a time runs its MUFU-bound phase; the other overlaps its barrier wait, TMEM load
+          // and arrive with it (named barriers 2+g carry the "XU token", 128 waiting + 128 arriving threads)
+          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
 #pragma unroll
           for (int c16 = 0; c16 < 8; ++c16) {
             uint4 q;
@@ -852,17 +856,18 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
               const int i = c16 * 8 + 2 * t;
               const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]);
               if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
-              qw[t] = pack_f16x2(ex2_approx(fmaf(s0, p.scale_log2, neg_m)), ex2_approx(fmaf(s1, p.scale_log2, neg_m)));
+              qw[t] = pack_f16x2_scaled(ex2_approx(fmaf(s0, p.scale_log2, neg_m)), ex2_approx(fmaf(s1, p.scale_log2, neg_m)));
             }
             *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
           }
+          if (pingpong) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (g ^ 1)) : "memory");
           const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
           if (tr) p.trace[j * 16 + 7] = clock64();
           if (j > 0 && __any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
             const float m_up = fmaxf(m_run, m_new);
             rescale_o(m_up);
             m_run = m_up;
-            neg_m = -m_run;
+            neg_m = -(m_run + kPackBias);
 #pragma unroll 1
             for (int c16 = 0; c16 < 8; ++c16) {
               uint4 q;
@@ -870,13 +875,14 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const int i = c16 * 8 + 2 * t;
-                qw[t] = pack_f16x2(ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)),
-                                   ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)));
+                qw[t] = pack_f16x2_scaled(ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)),
+                                          ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)));
               }
               *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
             }
           }
         } else {   // ragged tile (rare): plain two-phase version with per-element masking
+          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
           float mx = -INFINITY;
 #pragma unroll 1
           for (int i = 0; i < 64; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(s[i]));
@@ -901,6 +907,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
             }
             *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
           }
+          if (pingpong) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (g ^ 1)) : "memory");
         }
         if (tr) p.trace[j * 16 + 8] = clock64();
         fence_proxy_async_smem();

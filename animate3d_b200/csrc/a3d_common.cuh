@@ -172,6 +172,16 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
+// Pack two probabilities into an fp16 pair WITHOUT the XU-pipe F2FP conversion.  The caller evaluates
+// e = ex2(x - 112) = P * 2^-112 (flushed to 0 below 2^-126, i.e. P < 2^-14 = fp16 min normal); for such e the fp32 bit
+// pattern shifted right by 13 IS the fp16 bit pattern of P (exponent field E-112+... lines up, mantissa truncated), so
+// rounding is an integer add and the pack is shift/mask on the ALU + FMA pipes.  Valid for 0 <= P < 65536.
+__device__ __forceinline__ uint32_t pack_f16x2_scaled(float e_lo, float e_hi) {
+  const uint32_t lo = (__float_as_uint(e_lo) + 0x1000u) >> 13;
+  const uint32_t hi = (__float_as_uint(e_hi) * 8u + 0x8000u) & 0xFFFF0000u;
+  return hi | lo;
+}
+constexpr float kPackBias = 112.0f;
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));

@@ -67,11 +67,15 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStageOut = 0;
+  static constexpr int kStageOut = 2048;   // 2 x 256 fp32 bias values (double-buffered with the accumulator)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// EPI: 0 = bias/row-bias only, 1 = + residuals / row permutation, 2 = GEGLU, 3 = fp32 output (register pressure and dead
+// code differ enough that one runtime-branched epilogue spilled)
+enum { kEpiPlain = 0, kEpiRes = 1, kEpiGeglu = 2, kEpiF32 = 3 };
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
   using Cfg = GemmCfg<BN>;
@@ -186,16 +190,24 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       const bool row_ok = row < p.M;
       const int64_t rbrow = (p.rowbias && row_ok) ? ((row / p.rb_div) % p.rb_mod) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      const int64_t n_out = p.geglu ? p.N / 2 : p.N;
+      const int64_t n_out = (EPI == kEpiGeglu) ? p.N / 2 : p.N;
+      // the tile's BN bias values: one coalesced load by the 256 epilogue threads, then broadcast reads from shared memory
+      float* sb = reinterpret_cast<float*>(smem_stage) + acc * 256;
+      if (p.bias) {
+        const int64_t bc = (int64_t)nt * BN + threadIdx.x;
+        if (threadIdx.x < BN) sb[threadIdx.x] = bc < p.N ? __ldg(p.bias + bc) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
 
       // fp32 values of 32 accumulator columns -> + bias + rowbias, * scale
       auto finish32 = [&](uint32_t* r, int64_t col0) {
         float* v = reinterpret_cast<float*>(r);
         if (col0 + 32 <= p.N) {
           if (p.bias) {
+            const float4* bs = reinterpret_cast<const float4*>(sb + (col0 - (int64_t)nt * BN));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+              const float4 b = bs[i];
               v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
@@ -220,18 +232,18 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
         }
       };
-      const int64_t orow = row_ok ? perm_row(row, p.perm_a, p.perm_b) : 0;
+      const int64_t orow = (EPI == kEpiRes && row_ok) ? perm_row(row, p.perm_a, p.perm_b) : row;
       // 32 finished fp32 values of this thread's row -> (+ residuals) -> fp16 -> two 256-bit stores (two full sectors)
       auto store32 = [&](uint32_t* r, const uint32_t* r1, const uint32_t* r2, int64_t ocol) {
         float* v = reinterpret_cast<float*>(r);
-        if (p.R1) {
+        if (EPI == kEpiRes && p.R1) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r1[i]));
             v[2 * i] += p.r1_scale * f.x; v[2 * i + 1] += p.r1_scale * f.y;
           }
         }
-        if (p.R2) {
+        if (EPI == kEpiRes && p.R2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r2[i]));
@@ -262,7 +274,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         if (p.R2) { ld_global_256(p.R2 + orow * p.ldr2 + ocol, r2); ld_global_256(p.R2 + orow * p.ldr2 + ocol + 16, r2 + 8); }
       };
 
-      if (p.out_f32) {
+      if constexpr (EPI == kEpiF32) {
         // fp32 output (time-embedding table only)
         constexpr int U = BN / 32;
         const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
@@ -278,7 +290,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
             for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = __uint_as_float(r[i]);
           }
         }
-      } else if (!p.geglu) {
+      } else if constexpr (EPI != kEpiGeglu) {
         constexpr int U = BN / 32;                                  // 32-column units: 8 / 5 / 4
         const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
 #pragma unroll 1
@@ -287,7 +299,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           if (col0 >= p.N) break;
           uint32_t r[32], r1[16], r2[16];
           tmem_ld32(taddr + u * 32, r);
-          if (row_ok) load_res(r1, r2, col0);
+          if constexpr (EPI == kEpiRes) { if (row_ok) load_res(r1, r2, col0); }
           tmem_wait_ld();
           if (row_ok) {
             finish32(r, col0);
@@ -305,7 +317,6 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           uint32_t ru[32], rg[32], r1[16], r2[16];
           tmem_ld32(taddr + b * 64, ru);
           tmem_ld32(taddr + b * 64 + 32, rg);
-          if (row_ok) load_res(r1, r2, col0 / 2);
           tmem_wait_ld();
           if (row_ok) {
             finish32(ru, col0);
@@ -377,19 +388,27 @@ __global__ void gemm_simt_kernel(const GemmDev p, const __half* __restrict__ A, 
   else reinterpret_cast<__half*>(p.C)[orow * p.ldc + j] = __float2half_rn(v);
 }
 
-template <int BN>
-static int launch_tc(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, cudaStream_t st) {
+template <int BN, int EPI>
+static int launch_tc_epi(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    A3D_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = dev.tiles_m * dev.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN><<<grid, 320, Cfg::kSmemBytes, st>>>(dev, *mapA, *mapB);
+  gemm_tc_kernel<BN, EPI><<<grid, 320, Cfg::kSmemBytes, st>>>(dev, *mapA, *mapB);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
+}
+
+template <int BN>
+static int launch_tc(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, cudaStream_t st) {
+  if (dev.out_f32) return launch_tc_epi<BN, kEpiF32>(dev, mapA, mapB, st);
+  if (dev.geglu) return launch_tc_epi<BN, kEpiGeglu>(dev, mapA, mapB, st);
+  if (dev.R1 || dev.R2 || dev.perm_a) return launch_tc_epi<BN, kEpiRes>(dev, mapA, mapB, st);
+  return launch_tc_epi<BN, kEpiPlain>(dev, mapA, mapB, st);
 }
 
 }  // namespace a3d
@@ -411,8 +430,8 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   d.R2 = reinterpret_cast<const __half*>(a->R2); d.ldr2 = a->ldr2;
   d.C = a->C; d.ldc = a->ldc; d.geglu = a->geglu; d.out_f32 = a->out_f32;
   d.perm_a = a->perm_a; d.perm_b = a->perm_b;
-  if (a->geglu && (a->out_f32 || (a->N % 128)))
-    return fail(A3D_EINVAL, "a3d_gemm: GEGLU epilogue needs fp16 output and N %% 128 == 0");
+  if (a->geglu && (a->out_f32 || a->R1 || a->R2 || a->perm_a || (a->N % 128)))
+    return fail(A3D_EINVAL, "a3d_gemm: GEGLU epilogue takes bias / row-bias only, fp16 output, N %% 128 == 0");
   if (a->out_f32 && (a->R1 || a->R2 || a->perm_a))
     return fail(A3D_EINVAL, "a3d_gemm: fp32 output supports bias / row-bias only");
 
