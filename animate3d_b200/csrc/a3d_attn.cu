@@ -639,12 +639,18 @@ struct Attn3Cfg {
   static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + 1024 + 512;
 };
 
-template <int D>
+// MODE bits: [1:0] = how many of the 4 fp16x2 pairs of every 8-key chunk evaluate exp2 on the FMA pipe (Cody-Waite +
+// degree-3 minimax polynomial, rel. error 7.5e-5 << fp16 ulp) instead of MUFU.EX2 -- B200 retires only 8 MUFU ops per
+// clock per SM, which at head_dim 40 is *the* bound of the whole kernel (4.3e9 exponentials per level-0 launch = 2.0 ms);
+// [2] = fp16 packing on the ALU pipe (exponent-bias trick) instead of F2FP.
+template <int D, int MODE>
 __global__ void __launch_bounds__(384, 1)
 attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV) {
   using Cfg = Attn3Cfg<D>;
   constexpr int S = Cfg::kStages;
+  constexpr int kPoly = MODE & 3;
+  constexpr bool kPackAlu = (MODE >> 2) & 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -797,8 +803,6 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
       const uint32_t tmem_O = tmem_base + 256 + g * 64;
       float m_run = -INFINITY;
-      const bool pingpong = has1;       // both groups present -> alternate their MUFU phases
-      if (pingpong && g == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // group 0 owns the first turn
       const int rows_tile = p.k_box1 * p.k_box2;                  // keys a full tile holds (<= 64)
       const int keys_total = rows_tile * (n - 1) + p.rows_k;      // rows_k = valid keys of the LAST tile
       for (int j = 0; j < n; ++j) {
@@ -829,24 +833,29 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           }
           tmem_wait_st();
         };
-        if (valid == 64) {
-          // Single pass with a STALE stabiliser: P = exp2(s*c - m_run) uses the running max of the PREVIOUS steps, the max of
-          // this step is accumulated in the same loop (FMNMX3 on the ALU pipe hides under the MUFU-bound exponentials).
-          // Only when some row's new max exceeds the stabiliser by more than kRescaleLog2 (P could overflow fp16) is the
-          // step redone with the updated stabiliser -- after the first few steps that never happens.
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-          if (j == 0) {   // no stabiliser yet: real max first
+        // Ragged last tile: absent keys get a score of -inf (P = 0 on both exp paths); everything below is then shared.
+        if (valid < 64) {
 #pragma unroll
-            for (int i = 0; i < 64; i += 4) {
-              mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-              mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-            }
-            m_run = fmaxf(mx0, mx1) * p.scale_log2;
+          for (int i = 0; i < 64; ++i)
+            if (i >= valid) s[i] = 0xff800000u;
+        }
+        // Single pass with a STALE stabiliser: P = exp2(s*c - m_run) uses the running max of the PREVIOUS steps, the max of
+        // this step is accumulated in the same loop (FMNMX3 hides under the exponentials).  Only when some row's new max
+        // exceeds the stabiliser by more than kRescaleLog2 (P could overflow fp16) is the step redone with the updated
+        // stabiliser -- after the first few steps that never happens.  s[] is only ever indexed statically (registers).
+        if (j == 0) {   // no stabiliser yet: real max first
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
           }
-          float neg_m = -(m_run + kPackBias);
-          // ping-pong: only one group at a time runs its MUFU-bound phase; the other overlaps its barrier wait, TMEM load
-          // and arrive with it (named barriers 2+g carry the "XU token", 128 waiting + 128 arriving threads)
-          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
+          m_run = fmaxf(mx0, mx1) * p.scale_log2;
+        }
+#pragma unroll 1
+        for (int pass = 0;; ++pass) {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          const float neg_m = kPackAlu ? -(m_run + kPackBias) : -m_run;
 #pragma unroll
           for (int c16 = 0; c16 < 8; ++c16) {
             uint4 q;
@@ -856,59 +865,34 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
               const int i = c16 * 8 + 2 * t;
               const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]);
               if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
-              qw[t] = pack_f16x2_scaled(ex2_approx(fmaf(s0, p.scale_log2, neg_m)), ex2_approx(fmaf(s1, p.scale_log2, neg_m)));
-            }
-            *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
-          }
-          if (pingpong) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (g ^ 1)) : "memory");
-          const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
-          if (tr) p.trace[j * 16 + 7] = clock64();
-          if (j > 0 && __any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
-            const float m_up = fmaxf(m_run, m_new);
-            rescale_o(m_up);
-            m_run = m_up;
-            neg_m = -(m_run + kPackBias);
-#pragma unroll 1
-            for (int c16 = 0; c16 < 8; ++c16) {
-              uint4 q;
-              uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int i = c16 * 8 + 2 * t;
-                qw[t] = pack_f16x2_scaled(ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)),
-                                          ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)));
+              // P = exp2(s*c - m): MUFU for some pairs, FMA-pipe polynomial for the others (independent streams the
+              // scheduler interleaves): kPoly = 1 -> pair {1} of each chunk, 2 -> {1,3}, 3 -> {1,2,3}
+              const bool poly = kPoly == 1 ? (t == 1) : kPoly == 2 ? (t & 1) : kPoly == 3 ? (t != 0) : false;
+              float e0, e1;
+              if (poly) {
+                e0 = exp2_fma(fmaf(s0, p.scale_log2, -m_run));
+                e1 = exp2_fma(fmaf(s1, p.scale_log2, -m_run));
+                if (kPackAlu) { e0 *= 0x1p-112f; e1 *= 0x1p-112f; }
+              } else {
+                e0 = ex2_approx(fmaf(s0, p.scale_log2, neg_m));
+                e1 = ex2_approx(fmaf(s1, p.scale_log2, neg_m));
               }
-              *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
-            }
-          }
-        } else {   // ragged tile (rare): plain two-phase version with per-element masking
-          if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
-          float mx = -INFINITY;
-#pragma unroll 1
-          for (int i = 0; i < 64; ++i) if (i < valid) mx = fmaxf(mx, __uint_as_float(s[i]));
-          const float m_new = fmaxf(m_run, mx * p.scale_log2);
-          if (j == 0) {
-            m_run = m_new;
-          } else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
-            rescale_o(m_new);
-            m_run = m_new;
-          }
-          const float neg_m = -m_run;
-#pragma unroll 1
-          for (int c16 = 0; c16 < 8; ++c16) {
-            uint4 q;
-            uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int i = c16 * 8 + 2 * t;
-              const float p0 = i < valid ? ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, neg_m)) : 0.f;
-              const float p1 = i + 1 < valid ? ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, neg_m)) : 0.f;
-              qw[t] = pack_f16x2(p0, p1);
+              qw[t] = kPackAlu ? pack_f16x2_scaled(e0, e1) : pack_f16x2(e0, e1);
             }
             *reinterpret_cast<uint4*>(sPg + sw128_offset(r, c16)) = q;
           }
-          if (pingpong) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (g ^ 1)) : "memory");
+          if (pass == 0 && j > 0) {
+            const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
+            if (__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) {
+              const float m_up = fmaxf(m_run, m_new);
+              rescale_o(m_up);
+              m_run = m_up;
+              continue;
+            }
+          }
+          break;
         }
+        if (tr) p.trace[j * 16 + 7] = clock64();
         if (tr) p.trace[j * 16 + 8] = clock64();
         fence_proxy_async_smem();
         tc_fence_before();
@@ -1088,9 +1072,31 @@ static int tile_geom_k64(const a3d_view5& v, int* box1, int* box2, int* t1, int*
   return 0;
 }
 
+static int attn_mode() {   // see attn3_tc_kernel; A3D_ATTN_MODE is a tuning/debug override
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("A3D_ATTN_MODE");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
+template <int D, int MODE>
+static int launch_attn3_mode(const AttnDev& dev, const CUtensorMap* mq, const CUtensorMap* mk, const CUtensorMap* mv, dim3 grid,
+                             cudaStream_t st) {
+  using Cfg = Attn3Cfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn3_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  attn3_tc_kernel<D, MODE><<<grid, 384, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
 template <int D>
 static int launch_attn3(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
-  using Cfg = Attn3Cfg<D>;
   int kb1, kb2, kt1, ktiles, klast;
   if (int r = tile_geom_k64(a->k, &kb1, &kb2, &kt1, &ktiles, &klast)) return r;
   dev.kv_tiles = ktiles; dev.rows_k = klast; dev.k_t1 = kt1; dev.k_box1 = kb1; dev.k_box2 = kb2;
@@ -1098,15 +1104,16 @@ static int launch_attn3(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
   const CUtensorMap *mk, *mv;
   if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
   if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
-  static bool attr_set = false;
-  if (!attr_set) {
-    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn3_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
   grid.x = (grid.x + 1) / 2;
-  attn3_tc_kernel<D><<<grid, 384, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
-  A3D_LAUNCH_CHECK();
-  return A3D_OK;
+  switch (attn_mode()) {
+    case 0: return launch_attn3_mode<D, 0>(dev, mq, mk, mv, grid, st);
+    case 1: return launch_attn3_mode<D, 1>(dev, mq, mk, mv, grid, st);
+    case 2: return launch_attn3_mode<D, 2>(dev, mq, mk, mv, grid, st);
+    case 3: return launch_attn3_mode<D, 3>(dev, mq, mk, mv, grid, st);
+    case 6: return launch_attn3_mode<D, 6>(dev, mq, mk, mv, grid, st);
+    case 4: return launch_attn3_mode<D, 4>(dev, mq, mk, mv, grid, st);
+    default: return fail(A3D_EINVAL, "a3d_attention: A3D_ATTN_MODE %d not built (0,1,2,3,4,6)", attn_mode());
+  }
 }
 
 static long long* g_attn_trace = nullptr;

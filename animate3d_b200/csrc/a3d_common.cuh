@@ -162,6 +162,19 @@ __device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t* r) {
                : "memory");
 }
 // single-instruction math used by the softmax warps
+// 2^y on the FMA/ALU pipes only (no MUFU): y <= 127, flushes to ~1e-38 below -126.  Round-to-nearest split y = n + f with
+// the 1.5*2^23 magic constant (n lands in the low mantissa bits of t), degree-3 minimax polynomial for 2^f on [-0.5, 0.5]
+// (max relative error 7.5e-5), exponent added with one integer add.
+__device__ __forceinline__ float exp2_fma(float y) {
+  y = fmaxf(y, -126.0f);
+  const float t = y + 12582912.0f;
+  const float f = y - (t - 12582912.0f);
+  float r = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
+  r = fmaf(r, f, 0.6932609677314758f);
+  r = fmaf(r, f, 0.9999280571937561f);
+  return __uint_as_float(__float_as_uint(r) + (__float_as_uint(t) << 23));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

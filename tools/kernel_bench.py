@@ -81,6 +81,8 @@ if __name__ == "__main__":
         gemm_case("l2 conv3x3 1280->1280", M0 // 16, 1280, 11520, conv=(128, 8, 8, 1280, 1))
         gemm_case("l2 geglu 1280->10240", M0 // 16, 10240, 1280, geglu=True)
         gemm_case("up conv3x3 960->320", M0, 320, 8640, conv=(128, 32, 32, 960, 1))
+    if which == "attn0":
+        attn_case("l0 cross-view", 2, 4, 16, 1024, 40)
     if which in ("all", "attn"):
         attn_case("l0 cross-view", 2, 4, 16, 1024, 40)
         attn_case("l1 cross-view", 2, 4, 16, 256, 80)
