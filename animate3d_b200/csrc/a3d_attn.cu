@@ -668,7 +668,8 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
                                                // the MMA thread's poll, a single parity barrier would alias
   uint64_t* pv_done = p_full + 4;              // [2 groups][2 buffers]
   uint64_t* o_full = pv_done + 4;              // [2 groups]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;               // [2 groups][2 buffers]: S(j) is in the softmax warps' registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -698,6 +699,7 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
     for (int i = 0; i < 4; ++i) mbar_init(&pv_done[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&s_free[i], 4);
     mbar_init(&o_full[0], 1);
     mbar_init(&o_full[1], 1);
     mbar_fence_init();
@@ -774,24 +776,31 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         tc_fence_after();
         issue_qk(j0);
       }
+      // QK^T(j+2) only needs the S buffer of step j back, which the softmax warps release as soon as S(j) sits in their
+      // registers (start of their step j); PV(j) needs P(j) (end of their step j).  Issuing in that order keeps the
+      // score tiles two full steps ahead and takes this thread's wait -> issue -> commit latency off the critical path.
       for (int j = 0; j < n; ++j) {
-        const bool ahead = j + 2 < n;
-        mbar_wait(&p_full[2 * g + (j & 1)], (j >> 1) & 1);
         const bool tr = p.trace && g == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64;
-        if (tr) p.trace[j * 16 + 0] = clock64();
-        mbar_wait(&v_full[j % S], (j / S) & 1);
-        tc_fence_after();
-        issue_pv(j);
-        if (tr) p.trace[j * 16 + 1] = clock64();
-        if (ahead) {
+        if (j + 2 < n) {
+          mbar_wait(&s_free[2 * g + (j & 1)], (j >> 1) & 1);
+          if (tr) p.trace[j * 16 + 0] = clock64();
           mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
           tc_fence_after();
+          if (tr) p.trace[j * 16 + 10] = clock64();
           issue_qk(j + 2);
         }
+        if (tr) p.trace[j * 16 + 1] = clock64();
+        mbar_wait(&p_full[2 * g + (j & 1)], (j >> 1) & 1);
         if (tr) p.trace[j * 16 + 2] = clock64();
+        mbar_wait(&v_full[j % S], (j / S) & 1);
+        tc_fence_after();
+        if (tr) p.trace[j * 16 + 11] = clock64();
+        issue_pv(j);
+        if (tr) p.trace[j * 16 + 3] = clock64();
         // every MMA this warp issued so far (QK^T of steps <= j+2, PV of steps <= j) precedes these commits
         umma_commit(&v_empty[j % S]);
         umma_commit(&k_empty[j % S]);
+        if (tr) p.trace[j * 16 + 12] = clock64();
       }
       umma_commit(&o_full[g]);
     }
@@ -815,6 +824,9 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         uint32_t s[64];
         tmem_ld64(tmem_base + lane_addr + (2 * g + (j & 1)) * 64, s);
         tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[2 * g + (j & 1)]);   // S buffer may be overwritten by QK^T(j+2)
         if (tr) p.trace[j * 16 + 6] = clock64();
         uint8_t* sPg = sP + (2 * g + (j & 1)) * Cfg::kPBox;
         if (j >= 2) mbar_wait(&pv_done[2 * g + (j & 1)], ((j - 2) >> 1) & 1);   // P buffer of step j-2 consumed (long ago)

@@ -16,7 +16,9 @@ kb.attn_case("l0 cross-view (traced)", 2, 4, 16, 1024, 40)
 lib.a3d_debug_set_attn_trace(C.c_void_p(None))
 t = buf.cpu().view(64, 16)
 t0 = int(t[0, 4])
-names = {0: "mma:p_full", 1: "mma:pv_issued", 2: "mma:qk_issued", 4: "sm:wait_s", 5: "sm:got_s", 6: "sm:tmem_ld", 7: "sm:max", 8: "sm:exp_st", 9: "sm:arrive"}
-print("step  " + "  ".join(f"{names[k]:>13s}" for k in sorted(names)))
-for j in list(range(0, 12)) + [30, 31, 32, 62, 63]:
-    print(f"{j:4d}  " + "  ".join(f"{int(t[j, k]) - t0:13d}" for k in sorted(names)))
+names = {0: "m:s_free", 10: "m:k_ready", 1: "m:qk_iss", 2: "m:p_full", 11: "m:v_ready", 3: "m:pv_iss", 12: "m:commits",
+         4: "s:wait_s", 5: "s:got_s", 6: "s:tmem_ld", 7: "s:exp_done", 9: "s:arrive"}
+order = [0, 10, 1, 2, 11, 3, 12, 4, 5, 6, 7, 9]
+print("step " + " ".join(f"{names[k]:>10s}" for k in order))
+for j in list(range(0, 12)) + [30, 31, 32, 61]:
+    print(f"{j:4d} " + " ".join(f"{int(t[j, k]) - t0:10d}" for k in order))
