@@ -31,6 +31,7 @@ struct AttnDev {
   int accumulate;
   float out_scale;
   long long* trace;   // debug: per-step timestamps of CTA (0,0,0) (null in production)
+  int stagger;        // v3: cycles query tile 1's softmax warps hold back at step 0 (anti-phases the two tiles' MUFU bursts)
 };
 
 constexpr float kRescaleLog2 = 8.0f;
@@ -642,7 +643,10 @@ struct Attn3Cfg {
 // MODE bits: [1:0] = how many of the 4 fp16x2 pairs of every 8-key chunk evaluate exp2 on the FMA pipe (Cody-Waite +
 // degree-3 minimax polynomial, rel. error 7.5e-5 << fp16 ulp) instead of MUFU.EX2 -- B200 retires only 8 MUFU ops per
 // clock per SM, which at head_dim 40 is *the* bound of the whole kernel (4.3e9 exponentials per level-0 launch = 2.0 ms);
-// [2] = fp16 packing on the ALU pipe (exponent-bias trick) instead of F2FP.
+// [2] = fp16 packing on the ALU pipe (exponent-bias trick) instead of F2FP.  Measured on B200 (profiles/r01_pipes_ubench.txt,
+// profiles/r01_attn_modes.txt): MUFU.EX2 8 cycles and F2FP 4 cycles per warp instruction, FMNMX3/FFMA2 2 cycles; the
+// polynomial costs ~11 dispatch cycles per element, so modes 1/2 do not beat mode 0 (the default).  A bf16 P against an fp16 V
+// (mixed operand formats in one kind::f16 MMA) raises an illegal-instruction fault on sm_100a -- tried, removed.
 template <int D, int MODE>
 __global__ void __launch_bounds__(384, 1)
 attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -820,6 +824,14 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         if (tr) p.trace[j * 16 + 4] = clock64();
         mbar_wait(&s_full[2 * g + (j & 1)], (j >> 1) & 1);
         if (tr) p.trace[j * 16 + 5] = clock64();
+        if (j == 0 && g == 1 && p.stagger > 0) {
+          // The two tiles share each sub-partition's MUFU pipe.  Started together they stay in lock-step: both burn
+          // exponentials at half rate, then both sit in the barrier / TMEM-load / arrive part of the step with the pipe
+          // idle.  Half a step of offset is self-sustaining (whoever is alone on the pipe runs at full rate) and keeps
+          // the pipe busy through the other tile's bookkeeping.
+          const long long t_go = clock64() + p.stagger;
+          while (clock64() < t_go) __nanosleep(64);
+        }
         tc_fence_after();
         uint32_t s[64];
         tmem_ld64(tmem_base + lane_addr + (2 * g + (j & 1)) * 64, s);
@@ -968,6 +980,353 @@ attn3_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v4 (head_dim 40 and 80): v3's pipeline with SIXTEEN softmax warps.  Every 128-row query tile is served by 8 warps: the
+//   two warps that own a 32-row TMEM lane quadrant split the 64 keys of a step (32 columns each).  Four softmax warps
+//   per SM sub-partition instead of two: while one sits in its barrier / TMEM-load / arrive bookkeeping the other three
+//   keep the MUFU pipe (the bound at head_dim 40: 8 cycles per warp-wide ex2 + 4 per F2FP, profiles/r01_pipes_ubench.txt)
+//   busy, and 32 score registers per thread instead of 64 leave room for the compiler to software-pipeline the
+//   exponentials.  The two halves of a row keep ONE stabiliser m_run: they exchange their step maxima through shared
+//   memory + a 64-thread named barrier and reach the same rescale decision (both see the same 32 rows).
+//   TMEM: S[g][b] at column (2g+b)*64, O[g] at 256 + g*kOStride.
+//   Warps: 0-15 softmax (tile g = w>>3, half h = (w>>2)&1, quadrant w&3), 16/17 MMA issue for tile 0/1, 18 TMA, 19 TMEM.
+// ---------------------------------------------------------------------------------------------------------------
+template <int D>
+struct Attn4Cfg {
+  static constexpr int kDqk = (D + 15) / 16 * 16;
+  static constexpr int kDv = (D + 1 + 15) / 16 * 16;
+  static constexpr int kQB = (kDqk + 63) / 64;       // 64-column boxes per Q / K row
+  static constexpr int kVB = (kDv + 63) / 64;
+  static constexpr int kStages = (kQB == 1) ? 4 : 2;
+  static constexpr int kQBox = 128 * 128;            // 128 rows x 64 cols fp16
+  static constexpr int kKVBox = 64 * 128;            // 64 keys x 64 cols fp16
+  static constexpr int kSmemQ = 2 * kQB * kQBox;
+  static constexpr int kSmemK = kStages * kQB * kKVBox;
+  static constexpr int kSmemV = kStages * kVB * kKVBox;
+  static constexpr int kPBox = 128 * 128;            // 128 rows x 64 keys fp16
+  static constexpr int kSmemP = 2 * 2 * kPBox;       // [2 tiles][2 buffers]
+  static constexpr int kSmemMx = 3 * 2 * 2 * 128 * 4;   // [step parity | step-0 slot][tile][half][row] fp32 step maxima
+  static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + kSmemMx + 1024 + 512;
+  static constexpr int kOStride = (kDv <= 64) ? 64 : 128;
+  static_assert(256 + 2 * kOStride <= 512, "TMEM budget");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static constexpr int kOChunks = kDv / 16;                  // 16-column chunks of an O row
+  static constexpr int kOChunks0 = (kOChunks + 1) / 2;       // chunks half 0 owns (rescale + epilogue); half 1: the rest
+};
+
+// POLY: how many of the 4 fp16x2 pairs of every 8-key chunk take exp2 on the FMA pipe (exp2_fma) instead of MUFU.
+template <int D, int POLY>
+__global__ void __launch_bounds__(640, 1)
+attn4_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                const __grid_constant__ CUtensorMap mapV) {
+  using Cfg = Attn4Cfg<D>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kSmemQ;
+  uint8_t* sV = sK + Cfg::kSmemK;
+  uint8_t* sP = sV + Cfg::kSmemV;              // [2 tiles][2 buffers] 128 x 64 fp16, K-major, 128B-swizzled
+  float* sMx = reinterpret_cast<float*>(sP + Cfg::kSmemP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kSmemP + Cfg::kSmemMx);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;                 // [S]
+  uint64_t* v_full = k_full + S;               // [S]
+  uint64_t* k_empty = v_full + S;              // [S]
+  uint64_t* v_empty = k_empty + S;             // [S]
+  uint64_t* s_full = v_empty + S;              // [2 tiles][2 buffers]
+  uint64_t* s_free = s_full + 4;               // [2][2]  S(j) sits in the softmax warps' registers
+  uint64_t* p_full = s_free + 4;               // [2][2]
+  uint64_t* pv_done = p_full + 4;              // [2][2]
+  uint64_t* o_full = pv_done + 4;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt0 = blockIdx.x * 2;
+  const bool has1 = qt0 + 1 < p.q_tiles;
+  const int head = blockIdx.y;
+  const int qb = blockIdx.z;
+  const int n = p.kv_tiles;
+
+  if (p.rows_q < 128 || p.k_box1 * p.k_box2 < 64 || !has1) {
+    // partially filled tiles: rows TMA never writes must read as zeros (0 * garbage could be NaN in P V)
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    const int n16 = (Cfg::kSmemQ + Cfg::kSmemK + Cfg::kSmemV) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 18 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    const int tiles = has1 ? 2 : 1;
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], tiles);          // one commit per MMA-issuing warp
+      mbar_init(&v_empty[i], tiles);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&pv_done[i], 1);
+    }
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 19) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int q_i3 = qb % p.q_e3;
+  const int q_i4 = qb / p.q_e3;
+
+  if (warp == 18) {
+    if (lane == 0) {
+      const int kb = qb / p.kv_div;
+      const int k_i3 = p.kv_i3_zero ? 0 : (kb % p.k_e3);
+      const int k_i4 = kb / p.k_e3;
+      const int tiles = has1 ? 2 : 1;
+      mbar_expect_tx(q_full, p.q_box_bytes * (uint32_t)(tiles * Cfg::kQB));
+      for (int t = 0; t < tiles; ++t) {
+        const int qt = qt0 + t;
+#pragma unroll
+        for (int b = 0; b < Cfg::kQB; ++b)
+          tma_load_5d(sQ + (t * Cfg::kQB + b) * Cfg::kQBox, &mapQ, q_full, head * Cfg::kDqk + b * 64, (qt % p.q_t1) * p.q_box1,
+                      (qt / p.q_t1) * p.q_box2, q_i3, q_i4);
+      }
+      // K runs two steps ahead of V (QK^T(j+2) is issued during step j): interleave the issue order accordingly
+      auto load_k = [&](int j) {
+        const int st = j % S;
+        mbar_wait(&k_empty[st], ((j / S) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], p.k_box_bytes * Cfg::kQB);
+#pragma unroll
+        for (int b = 0; b < Cfg::kQB; ++b)
+          tma_load_5d(sK + (st * Cfg::kQB + b) * Cfg::kKVBox, &mapK, &k_full[st], head * Cfg::kDqk + b * 64,
+                      (j % p.k_t1) * p.k_box1, (j / p.k_t1) * p.k_box2, k_i3, k_i4);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % S;
+        mbar_wait(&v_empty[st], ((j / S) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], p.k_box_bytes * Cfg::kVB);
+#pragma unroll
+        for (int b = 0; b < Cfg::kVB; ++b)
+          tma_load_5d(sV + (st * Cfg::kVB + b) * Cfg::kKVBox, &mapV, &v_full[st], head * Cfg::kDv + b * 64,
+                      (j % p.k_t1) * p.k_box1, (j / p.k_t1) * p.k_box2, k_i3, k_i4);
+      };
+      if (n > 0) load_k(0);
+      if (n > 1) load_k(1);
+      for (int j = 0; j < n; ++j) {
+        if (j + 2 < n) load_k(j + 2);
+        load_v(j);
+      }
+    }
+  } else if (warp == 16 || warp == 17) {
+    const int g = warp - 16;
+    if (lane == 0 && (g == 0 || has1)) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
+      // descriptors differ only in the 14-bit (address >> 4) field: build the bases once, add offsets in the loop
+      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + g * Cfg::kQB * Cfg::kQBox), 16, 1024);
+      const uint64_t dk = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t dv = make_smem_desc_sw128(smem_u32(sV), Cfg::kKVBox, 1024);   // MN-major: next 64 columns one box on
+      const uint64_t dp = make_smem_desc_sw128(smem_u32(sP + 2 * g * Cfg::kPBox), 16, 1024);
+      const uint32_t tS = tmem_base + 2 * g * 64, tO = tmem_base + 256 + g * Cfg::kOStride;
+      auto issue_qk = [&](int j) {      // S[g][j&1] = Q_g K_j^T; the K stage is released as soon as these MMAs retire
+        const uint64_t kb_ = dk + (uint64_t)((j % S) * ((Cfg::kQB * Cfg::kKVBox) >> 4));
+#pragma unroll
+        for (int kk = 0; kk < Cfg::kDqk / 16; ++kk)
+          umma_f16(tS + (j & 1) * 64, dq + (uint64_t)((kk / 4) * (Cfg::kQBox >> 4) + 2 * (kk % 4)),
+                   kb_ + (uint64_t)((kk / 4) * (Cfg::kKVBox >> 4) + 2 * (kk % 4)), idesc_qk, kk ? 1u : 0u);
+        umma_commit(&s_full[2 * g + (j & 1)]);
+        umma_commit(&k_empty[j % S]);
+      };
+      auto issue_pv = [&](int j) {      // O_g += P_g(j) V_j
+        const uint64_t pb_ = dp + (uint64_t)((j & 1) * (Cfg::kPBox >> 4));
+        const uint64_t vb_ = dv + (uint64_t)((j % S) * ((Cfg::kVB * Cfg::kKVBox) >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tO, pb_ + (uint64_t)(2 * kk), vb_ + (uint64_t)(128 * kk), idesc_pv, (j | kk) ? 1u : 0u);
+        umma_commit(&pv_done[2 * g + (j & 1)]);
+        umma_commit(&v_empty[j % S]);
+      };
+      mbar_wait(q_full, 0);
+      for (int j0 = 0; j0 < 2 && j0 < n; ++j0) {
+        mbar_wait(&k_full[j0 % S], (j0 / S) & 1);
+        tc_fence_after();
+        issue_qk(j0);
+      }
+      for (int j = 0; j < n; ++j) {
+        if (j + 2 < n) {
+          mbar_wait(&s_free[2 * g + (j & 1)], (j >> 1) & 1);
+          mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
+          tc_fence_after();
+          issue_qk(j + 2);
+        }
+        mbar_wait(&p_full[2 * g + (j & 1)], (j >> 1) & 1);
+        mbar_wait(&v_full[j % S], (j / S) & 1);
+        tc_fence_after();
+        issue_pv(j);
+      }
+      umma_commit(&o_full[g]);
+    } else if (lane == 0 && n > 0) {
+      // tile 1 absent: nothing to issue, and k_empty / v_empty were initialised for a single committer
+    }
+  } else if (warp < 16) {
+    const int g = warp >> 3;
+    if (g == 0 || has1) {
+      const int h = (warp >> 2) & 1;
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+      const uint32_t tmem_O = tmem_base + 256 + g * Cfg::kOStride;
+      const int pair_bar = 1 + g * 4 + quad;       // named barrier shared with the warp that owns the other 32 keys
+      float m_run = -INFINITY;
+      const int rows_tile = p.k_box1 * p.k_box2;   // keys a full tile holds (<= 64)
+      // 16-column chunks of O this half rescales / writes out
+      const int oc0 = h ? Cfg::kOChunks0 : 0, oc1 = h ? Cfg::kOChunks : Cfg::kOChunks0;
+      for (int j = 0; j < n; ++j) {
+        const int valid = ((j == n - 1) ? p.rows_k : rows_tile) - 32 * h;   // valid keys among this half's 32 columns
+        const int b = 2 * g + (j & 1);
+        mbar_wait(&s_full[b], (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t s[32];
+        tmem_ld32(tmem_base + lane_addr + b * 64 + 32 * h, s);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[b]);   // S buffer may be overwritten by QK^T(j+2)
+        if (valid < 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= valid) s[i] = 0xff800000u;    // absent key: score -inf -> P = 0
+        }
+        float* mx_mine = sMx + (((j & 1) * 2 + g) * 2 + h) * 128 + r;
+        float* mx_other = sMx + (((j & 1) * 2 + g) * 2 + (h ^ 1)) * 128 + r;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+        if (j == 0) {   // no stabiliser yet: the real row maximum first
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          }
+          const float mloc = fmaxf(mx0, mx1);
+          sMx[((4 + g) * 2 + h) * 128 + r] = mloc;           // slot 2: written once, so no reuse hazard
+          pair_sync();
+          m_run = fmaxf(mloc, sMx[((4 + g) * 2 + (h ^ 1)) * 128 + r]) * p.scale_log2;
+        }
+        uint8_t* sPg = sP + b * Cfg::kPBox;
+        if (j >= 2) mbar_wait(&pv_done[b], ((j - 2) >> 1) & 1);   // P buffer of step j-2 consumed (long ago)
+#pragma unroll 1
+        for (int pass = 0;; ++pass) {
+          // Single pass with a STALE stabiliser (the running max of the previous steps); this step's max is accumulated in
+          // the same loop.  Only when a row's new max exceeds the stabiliser by more than kRescaleLog2 (P could overflow
+          // fp16) is the step redone with the updated stabiliser -- after the first few steps that never happens.
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          const float neg_m = -m_run;
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            uint4 q;
+            uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = c16 * 8 + 2 * t;
+              const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]);
+              if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
+              const bool poly = POLY == 1 ? (t == 1) : POLY == 2 ? (t & 1) : false;
+              const float y0 = fmaf(s0, p.scale_log2, neg_m), y1 = fmaf(s1, p.scale_log2, neg_m);
+              qw[t] = poly ? pack_f16x2(exp2_fma(y0), exp2_fma(y1)) : pack_f16x2(ex2_approx(y0), ex2_approx(y1));
+            }
+            *reinterpret_cast<uint4*>(sPg + sw128_offset(r, 4 * h + c16)) = q;
+          }
+          if (pass > 0 || j == 0) break;
+          *mx_mine = fmaxf(mx0, mx1);
+          pair_sync();
+          const float m_new = fmaxf(fmaxf(mx0, mx1), *mx_other) * p.scale_log2;   // identical in both halves of the row
+          if (!__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) break;
+          // rare: O_g must be stable -> PV of the previous step has to be complete; each half rescales its O chunks
+          const float m_up = fmaxf(m_run, m_new);
+          mbar_wait(&pv_done[2 * g + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          const float alpha = ex2_approx(m_run - m_up);
+#pragma unroll 1
+          for (int c = oc0; c < oc1; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_addr + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_addr + c * 16, o);
+          }
+          tmem_wait_st();
+          m_run = m_up;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[b]);
+      }
+      // ---- epilogue: this half writes its chunks of the normalised rows
+      mbar_wait(&o_full[g], 0);
+      tc_fence_after();
+      float inv;
+      {
+        uint32_t o[16];
+        tmem_ld16(tmem_O + lane_addr + (D / 16) * 16, o);
+        tmem_wait_ld();
+        inv = p.out_scale / __uint_as_float(o[D % 16]);
+      }
+      const int qt = qt0 + g;
+      const int q_i1 = (qt % p.q_t1) * p.q_box1, q_i2 = (qt / p.q_t1) * p.q_box2;
+      const bool row_ok = r < p.rows_q;
+      const int i1 = q_i1 + r % p.q_box1;
+      const int i2 = q_i2 + r / p.q_box1;
+      __half* orow = p.out + (int64_t)i1 * p.os1 + (int64_t)i2 * p.os2 + (int64_t)q_i3 * p.os3 + (int64_t)q_i4 * p.os4 + head * D;
+#pragma unroll 1
+      for (int c = oc0; c < oc1; ++c) {
+        if (c * 16 >= D) break;
+        uint32_t o[16];
+        tmem_ld16(tmem_O + lane_addr + c * 16, o);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            if (c * 16 + gq * 8 < D) {
+              uint4 q;
+              __half2* hh = reinterpret_cast<__half2*>(&q);
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(o[gq * 8 + t]) * inv;
+              if (p.accumulate) {
+                const uint4 old = *reinterpret_cast<const uint4*>(orow + c * 16 + gq * 8);
+                const __half2* ho = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(ho[t]);
+                  v[2 * t] += f.x;
+                  v[2 * t + 1] += f.y;
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 4; ++t) hh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+              *reinterpret_cast<uint4*>(orow + c * 16 + gq * 8) = q;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 19) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // SIMT bring-up / reference kernel (one thread per (batch, head, query)); same view semantics, fp32 math
 // ---------------------------------------------------------------------------------------------------------------
 struct ViewDev {
@@ -1016,6 +1375,107 @@ __global__ void attn_simt_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, i
     float o = out_scale * acc[c] / sum;
     if (accumulate) o += __half2float(op[c]);
     op[c] = __float2half_rn(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Few-keys attention (IP-adapter image tokens: 4 keys per image group).  The tensor path would spend a whole CTA
+// life-cycle (TMEM allocation, barrier set-up, TMA round trips) on one 64-key step that is 94% padding; the work itself
+// is a read of Q and a read-modify-write of the output.  One thread per (query row, head): fp32 math, 16-byte loads,
+// K/V of the image group stay in L1.  HBM-bound: ~(|Q| + 2|out|) bytes.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFewKeysMax = 8;
+
+__global__ void __launch_bounds__(256)
+attn_fewkeys_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, int64_t os1, int64_t os2, int64_t os3, int64_t os4, int heads,
+                    int d, int dqk, int dv, float scale_log2, int kv_div, int kv_i3_zero, int accumulate, float out_scale) {
+  const int Lq = q.e1 * q.e2, Lk = k.e1 * k.e2;
+  const int64_t total = (int64_t)q.e3 * q.e4 * Lq * heads;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int h = (int)(idx % heads);
+  const int64_t row = idx / heads;
+  const int l = (int)(row % Lq);
+  const int qb = (int)(row / Lq);
+  const int kb = qb / kv_div;
+  const __half* qp = q.base + (int64_t)(l % q.e1) * q.s1 + (int64_t)(l / q.e1) * q.s2 + (int64_t)(qb % q.e3) * q.s3 +
+                     (int64_t)(qb / q.e3) * q.s4 + h * dqk;
+  const int64_t koff = (int64_t)(kv_i3_zero ? 0 : kb % k.e3) * k.s3 + (int64_t)(kb / k.e3) * k.s4 + h * dqk;
+  const int64_t voff = (int64_t)(kv_i3_zero ? 0 : kb % v.e3) * v.s3 + (int64_t)(kb / v.e3) * v.s4 + h * dv;
+  int64_t krow[kFewKeysMax], vrow[kFewKeysMax];
+#pragma unroll
+  for (int j = 0; j < kFewKeysMax; ++j) {
+    const int jj = j < Lk ? j : 0;
+    krow[j] = koff + (int64_t)(jj % k.e1) * k.s1 + (int64_t)(jj / k.e1) * k.s2;
+    vrow[j] = voff + (int64_t)(jj % v.e1) * v.s1 + (int64_t)(jj / v.e1) * v.s2;
+  }
+  float sc[kFewKeysMax];
+#pragma unroll
+  for (int j = 0; j < kFewKeysMax; ++j) sc[j] = 0.f;
+  for (int c = 0; c < d; c += 8) {
+    const uint4 qv = *reinterpret_cast<const uint4*>(qp + c);
+    const __half2* qh = reinterpret_cast<const __half2*>(&qv);
+    float2 qf[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) qf[t] = __half22float2(qh[t]);
+#pragma unroll
+    for (int j = 0; j < kFewKeysMax; ++j) {
+      if (j < Lk) {
+        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(k.base + krow[j] + c));
+        const __half2* kh = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 kf = __half22float2(kh[t]);
+          sc[j] = fmaf(qf[t].x, kf.x, fmaf(qf[t].y, kf.y, sc[j]));
+        }
+      }
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kFewKeysMax; ++j)
+    if (j < Lk) m = fmaxf(m, sc[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kFewKeysMax; ++j) {
+    sc[j] = j < Lk ? exp2f((sc[j] - m) * scale_log2) : 0.f;
+    sum += sc[j];
+  }
+  const float inv = out_scale / sum;
+  __half* op = out + (int64_t)(l % q.e1) * os1 + (int64_t)(l / q.e1) * os2 + (int64_t)(qb % q.e3) * os3 +
+               (int64_t)(qb / q.e3) * os4 + h * d;
+  for (int c = 0; c < d; c += 8) {
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kFewKeysMax; ++j) {
+      if (j < Lk) {
+        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(v.base + vrow[j] + c));
+        const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 vf = __half22float2(vh[t]);
+          acc[2 * t] = fmaf(sc[j], vf.x, acc[2 * t]);
+          acc[2 * t + 1] = fmaf(sc[j], vf.y, acc[2 * t + 1]);
+        }
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+    if (accumulate) {
+      const uint4 old = *reinterpret_cast<const uint4*>(op + c);
+      const __half2* ho = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(ho[t]);
+        oh[t] = __floats2half2_rn(fmaf(acc[2 * t], inv, f.x), fmaf(acc[2 * t + 1], inv, f.y));
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) oh[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+    }
+    *reinterpret_cast<uint4*>(op + c) = o;
   }
 }
 
@@ -1084,11 +1544,20 @@ static int tile_geom_k64(const a3d_view5& v, int* box1, int* box2, int* t1, int*
   return 0;
 }
 
+static int attn_stagger() {   // cycles; A3D_ATTN_STAGGER overrides for tuning
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("A3D_ATTN_STAGGER");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static int attn_mode() {   // see attn3_tc_kernel; A3D_ATTN_MODE is a tuning/debug override
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("A3D_ATTN_MODE");
-    v = e ? atoi(e) : 2;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }
@@ -1117,15 +1586,35 @@ static int launch_attn3(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
   if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
   if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
   grid.x = (grid.x + 1) / 2;
+  dev.stagger = attn_stagger();
   switch (attn_mode()) {
     case 0: return launch_attn3_mode<D, 0>(dev, mq, mk, mv, grid, st);
     case 1: return launch_attn3_mode<D, 1>(dev, mq, mk, mv, grid, st);
     case 2: return launch_attn3_mode<D, 2>(dev, mq, mk, mv, grid, st);
-    case 3: return launch_attn3_mode<D, 3>(dev, mq, mk, mv, grid, st);
-    case 6: return launch_attn3_mode<D, 6>(dev, mq, mk, mv, grid, st);
     case 4: return launch_attn3_mode<D, 4>(dev, mq, mk, mv, grid, st);
-    default: return fail(A3D_EINVAL, "a3d_attention: A3D_ATTN_MODE %d not built (0,1,2,3,4,6)", attn_mode());
+    default: return fail(A3D_EINVAL, "a3d_attention: A3D_ATTN_MODE %d not built (0,1,2,4)", attn_mode());
   }
+}
+
+template <int D, int POLY>
+static int launch_attn4(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
+  using Cfg = Attn4Cfg<D>;
+  int kb1, kb2, kt1, ktiles, klast;
+  if (int r = tile_geom_k64(a->k, &kb1, &kb2, &kt1, &ktiles, &klast)) return r;
+  dev.kv_tiles = ktiles; dev.rows_k = klast; dev.k_t1 = kt1; dev.k_box1 = kb1; dev.k_box2 = kb2;
+  dev.k_box_bytes = 128u * (uint32_t)(kb1 * kb2);
+  const CUtensorMap *mk, *mv;
+  if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
+  if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn4_tc_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  grid.x = (grid.x + 1) / 2;
+  attn4_tc_kernel<D, POLY><<<grid, 640, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
 }
 
 static long long* g_attn_trace = nullptr;
@@ -1134,7 +1623,16 @@ static int attn_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("A3D_ATTN_VARIANT");
-    v = e ? atoi(e) : 3;
+    v = e ? atoi(e) : 4;
+  }
+  return v;
+}
+
+static int attn_variant80() {   // head_dim 80 through the v4 kernel (A3D_ATTN_V80=0 falls back to v1)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("A3D_ATTN_V80");
+    v = e ? atoi(e) : 1;
   }
   return v;
 }
@@ -1169,6 +1667,24 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
     return A3D_OK;
   }
 
+  if ((a->os1 | a->os2 | a->os3 | a->os4) % 8 || (reinterpret_cast<uintptr_t>(a->out) & 15))
+    return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
+  if (a->k.e1 * a->k.e2 <= kFewKeysMax) {
+    // a handful of keys (IP-adapter image tokens): HBM-bound thread-per-(row, head) kernel, see attn_fewkeys_kernel
+    if ((a->q.s1 | a->q.s2 | a->q.s3 | a->q.s4 | a->k.s1 | a->k.s2 | a->k.s3 | a->k.s4 | a->v.s1 | a->v.s2 | a->v.s3 | a->v.s4) % 8 ||
+        ((reinterpret_cast<uintptr_t>(a->q.base) | reinterpret_cast<uintptr_t>(a->k.base) | reinterpret_cast<uintptr_t>(a->v.base)) & 15))
+      return fail(A3D_EINVAL, "a3d_attention: operand rows must be 16-byte aligned");
+    ViewDev q{reinterpret_cast<const __half*>(a->q.base), a->q.s1, a->q.s2, a->q.s3, a->q.s4, a->q.e1, a->q.e2, a->q.e3, a->q.e4};
+    ViewDev k{reinterpret_cast<const __half*>(a->k.base), a->k.s1, a->k.s2, a->k.s3, a->k.s4, a->k.e1, a->k.e2, a->k.e3, a->k.e4};
+    ViewDev v{reinterpret_cast<const __half*>(a->v.base), a->v.s1, a->v.s2, a->v.s3, a->v.s4, a->v.e1, a->v.e2, a->v.e3, a->v.e4};
+    const int64_t total = (int64_t)batches * a->heads * a->q.e1 * a->q.e2;
+    attn_fewkeys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        q, k, v, reinterpret_cast<__half*>(a->out), a->os1, a->os2, a->os3, a->os4, a->heads, d, dqk, dv,
+        a->scale * 1.4426950408889634f, kv_div, a->kv_i3_zero, a->accumulate, a->out_scale == 0.f ? 1.f : a->out_scale);
+    A3D_LAUNCH_CHECK();
+    return A3D_OK;
+  }
+
   AttnDev dev;
   memset(&dev, 0, sizeof(dev));
   int qb1, qb2, qt1, qtiles, qrows, kb1, kb2, kt1, ktiles, krows;
@@ -1198,8 +1714,13 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
     case 40:
       if (attn_variant() == 1) return launch_attn<40>(dev, mq, mk, mv, grid, st);
       if (attn_variant() == 2) return launch_attn2<40>(dev, mq, mk, mv, grid, st);
-      return launch_attn3<40>(dev, a, mq, grid, st);
-    case 80: return launch_attn<80>(dev, mq, mk, mv, grid, st);
+      if (attn_variant() == 3) return launch_attn3<40>(dev, a, mq, grid, st);
+      if (attn_mode() == 1) return launch_attn4<40, 1>(dev, a, mq, grid, st);
+      if (attn_mode() == 2) return launch_attn4<40, 2>(dev, a, mq, grid, st);
+      return launch_attn4<40, 0>(dev, a, mq, grid, st);
+    case 80:
+      if (attn_variant() >= 4 && attn_variant80()) return launch_attn4<80, 0>(dev, a, mq, grid, st);
+      return launch_attn<80>(dev, mq, mk, mv, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
   }
 }

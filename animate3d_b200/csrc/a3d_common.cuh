@@ -237,10 +237,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= (uint64_t)2 << 61;  // layout_type = SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16 with fp16 A/B and fp32 accumulate.
-__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
+// Instruction descriptor for kind::f16 with fp16 (or, per operand, bf16) A/B and fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major,
+                                                      bool a_bf16 = false, bool b_bf16 = false) {
   return (1u << 4)                          // c_format = F32
-         | (0u << 7) | (0u << 10)           // a_format = b_format = F16
+         | ((a_bf16 ? 1u : 0u) << 7)        // a_format: 0 = F16, 1 = BF16
+         | ((b_bf16 ? 1u : 0u) << 10)       // b_format
          | ((a_mn_major ? 1u : 0u) << 15)   // a_major
          | ((b_mn_major ? 1u : 0u) << 16)   // b_major
          | ((N >> 3) << 17)                 // n_dim

@@ -241,7 +241,8 @@ def test_cross_view_attention(case, impl, layout):
 
 
 @pytest.mark.parametrize("impl", ["tc", "simt"])
-@pytest.mark.parametrize("case", [(2, 3, 1024, 40, 77), (2, 2, 256, 80, 77), (3, 2, 64, 160, 4), (2, 2, 16, 160, 77)],
+@pytest.mark.parametrize("case", [(2, 3, 1024, 40, 77), (2, 2, 256, 80, 77), (3, 2, 64, 160, 4), (2, 2, 16, 160, 77),
+                                  (2, 3, 1024, 40, 4), (3, 2, 256, 80, 4), (2, 2, 64, 160, 8), (2, 2, 256, 40, 16)],
                          ids=lambda c: "bn%d_f%d_hw%d_d%d_k%d" % c)
 def test_cross_attention_text_keys(case, impl):
     """attn2 of the spatial transformers: queries [(bn f), hw], keys [bn, Lk] shared by the F frames (kv_div = F)."""
@@ -270,6 +271,11 @@ def test_cross_attention_text_keys(case, impl):
     ref = ref.permute(0, 2, 1, 3).reshape(rows, C)
     torch.cuda.synchronize()
     close(out, ref, what=f"cross attention {case} {impl}")
+    # IP-adapter use: a second key set accumulated onto the first result with a scale (attention_processor.py:218-238)
+    ops.attention(vq, vk, vv, out, (C, hw * C, hw * C, Fr * hw * C), heads=heads, d=d, scale=scale, kv_div=Fr,
+                  accumulate=True, out_scale=0.25, impl=L.IMPL_TC if impl == "tc" else L.IMPL_SIMT)
+    torch.cuda.synchronize()
+    close(out, 1.25 * ref, what=f"accumulated cross attention {case} {impl}")
 
 
 # ------------------------------------------------------------------------------------------------------------ ops
