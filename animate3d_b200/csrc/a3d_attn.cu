@@ -1327,6 +1327,360 @@ attn4_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v5 (head_dim 40): v4 with the two key halves of a step made INDEPENDENT.  In v4 the two warps that share a 32-row
+//   quadrant keep one stabiliser and meet at a named barrier every step; both sit on the same SM sub-partition, so they
+//   behave like one 64-key warp and the MUFU pipe still idles ~37% of the time (profiles/r01_ncu_attn4.txt).  Here each half
+//   owns a full online-softmax state: its own stabiliser, its own O accumulator in TMEM (4 x 64 columns fit next to the
+//   4 x 64 score columns only at head_dim 40) and its own P-ready barrier; PV is issued per half (K = 32 keys).  The two
+//   partial results of a row are merged once, in the epilogue: O = (w0 O0 + w1 O1) / (w0 l0 + w1 l1), w_h = 2^(m_h - m).
+//   TMEM: S[g][b] at column (2g+b)*64, O[g][h] at 256 + (2g+h)*64.
+// ---------------------------------------------------------------------------------------------------------------
+template <int D>
+struct Attn5Cfg {
+  static constexpr int kDqk = (D + 15) / 16 * 16;
+  static constexpr int kDv = (D + 1 + 15) / 16 * 16;
+  static constexpr int kQB = (kDqk + 63) / 64;       // 64-column boxes per Q / K row
+  static constexpr int kVB = (kDv + 63) / 64;
+  static constexpr int kStages = (kQB == 1) ? 4 : 2;
+  static constexpr int kQBox = 128 * 128;            // 128 rows x 64 cols fp16
+  static constexpr int kKVBox = 64 * 128;            // 64 keys x 64 cols fp16
+  static constexpr int kSmemQ = 2 * kQB * kQBox;
+  static constexpr int kSmemK = kStages * kQB * kKVBox;
+  static constexpr int kSmemV = kStages * kVB * kKVBox;
+  static constexpr int kPBox = 128 * 128;            // 128 rows x 64 keys fp16
+  static constexpr int kSmemP = 2 * 2 * kPBox;       // [2 tiles][2 buffers]
+  static constexpr int kSmemMx = 2 * 2 * 128 * 4;       // [tile][half][row] final stabilisers (epilogue merge)
+  static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + kSmemMx + 1024 + 512;
+  static_assert(kDv <= 64 && kQB == 1 && kVB == 1, "v5 keeps four O accumulators in TMEM: head_dim <= 47 only");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static constexpr int kOChunks = kDv / 16;                  // 16-column chunks of an O row
+  static constexpr int kOChunks0 = (kOChunks + 1) / 2;       // chunks half 0 owns (rescale + epilogue); half 1: the rest
+};
+
+// POLY: how many of the 4 fp16x2 pairs of every 8-key chunk take exp2 on the FMA pipe (exp2_fma) instead of MUFU.
+template <int D, int POLY>
+__global__ void __launch_bounds__(640, 1)
+attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                const __grid_constant__ CUtensorMap mapV) {
+  using Cfg = Attn5Cfg<D>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kSmemQ;
+  uint8_t* sV = sK + Cfg::kSmemK;
+  uint8_t* sP = sV + Cfg::kSmemV;              // [2 tiles][2 buffers] 128 x 64 fp16, K-major, 128B-swizzled
+  float* sMx = reinterpret_cast<float*>(sP + Cfg::kSmemP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kSmemP + Cfg::kSmemMx);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;                 // [S]
+  uint64_t* v_full = k_full + S;               // [S]
+  uint64_t* k_empty = v_full + S;              // [S]
+  uint64_t* v_empty = k_empty + S;             // [S]
+  uint64_t* s_full = v_empty + S;              // [2 tiles][2 buffers]
+  uint64_t* s_free = s_full + 4;               // [2][2]  S(j) sits in the softmax warps' registers
+  uint64_t* p_full = s_free + 4;               // [2 tiles][2 halves][2 buffers]
+  uint64_t* pv_done = p_full + 8;              // [2][2][2]
+  uint64_t* o_full = pv_done + 8;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt0 = blockIdx.x * 2;
+  const bool has1 = qt0 + 1 < p.q_tiles;
+  const int head = blockIdx.y;
+  const int qb = blockIdx.z;
+  const int n = p.kv_tiles;
+
+  if (p.rows_q < 128 || p.k_box1 * p.k_box2 < 64 || !has1) {
+    // partially filled tiles: rows TMA never writes must read as zeros (0 * garbage could be NaN in P V)
+    uint4* z = reinterpret_cast<uint4*>(sQ);
+    const int n16 = (Cfg::kSmemQ + Cfg::kSmemK + Cfg::kSmemV) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 18 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    const int tiles = has1 ? 2 : 1;
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&k_empty[i], tiles);          // one commit per MMA-issuing warp
+      mbar_init(&v_empty[i], tiles);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 8);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 19) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int q_i3 = qb % p.q_e3;
+  const int q_i4 = qb / p.q_e3;
+
+  if (warp == 18) {
+    if (lane == 0) {
+      const int kb = qb / p.kv_div;
+      const int k_i3 = p.kv_i3_zero ? 0 : (kb % p.k_e3);
+      const int k_i4 = kb / p.k_e3;
+      const int tiles = has1 ? 2 : 1;
+      mbar_expect_tx(q_full, p.q_box_bytes * (uint32_t)(tiles * Cfg::kQB));
+      for (int t = 0; t < tiles; ++t) {
+        const int qt = qt0 + t;
+#pragma unroll
+        for (int b = 0; b < Cfg::kQB; ++b)
+          tma_load_5d(sQ + (t * Cfg::kQB + b) * Cfg::kQBox, &mapQ, q_full, head * Cfg::kDqk + b * 64, (qt % p.q_t1) * p.q_box1,
+                      (qt / p.q_t1) * p.q_box2, q_i3, q_i4);
+      }
+      // K runs two steps ahead of V (QK^T(j+2) is issued during step j): interleave the issue order accordingly
+      auto load_k = [&](int j) {
+        const int st = j % S;
+        mbar_wait(&k_empty[st], ((j / S) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], p.k_box_bytes * Cfg::kQB);
+#pragma unroll
+        for (int b = 0; b < Cfg::kQB; ++b)
+          tma_load_5d(sK + (st * Cfg::kQB + b) * Cfg::kKVBox, &mapK, &k_full[st], head * Cfg::kDqk + b * 64,
+                      (j % p.k_t1) * p.k_box1, (j / p.k_t1) * p.k_box2, k_i3, k_i4);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % S;
+        mbar_wait(&v_empty[st], ((j / S) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], p.k_box_bytes * Cfg::kVB);
+#pragma unroll
+        for (int b = 0; b < Cfg::kVB; ++b)
+          tma_load_5d(sV + (st * Cfg::kVB + b) * Cfg::kKVBox, &mapV, &v_full[st], head * Cfg::kDv + b * 64,
+                      (j % p.k_t1) * p.k_box1, (j / p.k_t1) * p.k_box2, k_i3, k_i4);
+      };
+      if (n > 0) load_k(0);
+      if (n > 1) load_k(1);
+      for (int j = 0; j < n; ++j) {
+        if (j + 2 < n) load_k(j + 2);
+        load_v(j);
+      }
+    }
+  } else if (warp == 16 || warp == 17) {
+    const int g = warp - 16;
+    if (lane == 0 && (g == 0 || has1)) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
+      // descriptors differ only in the 14-bit (address >> 4) field: build the bases once, add offsets in the loop
+      const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + g * Cfg::kQB * Cfg::kQBox), 16, 1024);
+      const uint64_t dk = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t dv = make_smem_desc_sw128(smem_u32(sV), Cfg::kKVBox, 1024);   // MN-major: next 64 columns one box on
+      const uint64_t dp = make_smem_desc_sw128(smem_u32(sP + 2 * g * Cfg::kPBox), 16, 1024);
+      const uint32_t tS = tmem_base + 2 * g * 64, tO = tmem_base + 256 + 2 * g * 64;
+      auto issue_qk = [&](int j) {      // S[g][j&1] = Q_g K_j^T; the K stage is released as soon as these MMAs retire
+        const uint64_t kb_ = dk + (uint64_t)((j % S) * ((Cfg::kQB * Cfg::kKVBox) >> 4));
+#pragma unroll
+        for (int kk = 0; kk < Cfg::kDqk / 16; ++kk)
+          umma_f16(tS + (j & 1) * 64, dq + (uint64_t)((kk / 4) * (Cfg::kQBox >> 4) + 2 * (kk % 4)),
+                   kb_ + (uint64_t)((kk / 4) * (Cfg::kKVBox >> 4) + 2 * (kk % 4)), idesc_qk, kk ? 1u : 0u);
+        umma_commit(&s_full[2 * g + (j & 1)]);
+        umma_commit(&k_empty[j % S]);
+      };
+      auto issue_pv = [&](int j, int hh) {      // O_g,hh += P_g(j)[:, 32 hh .. 32 hh + 31] V_j[32 hh .. 32 hh + 31, :]
+        const uint64_t pb_ = dp + (uint64_t)((j & 1) * (Cfg::kPBox >> 4));
+        const uint64_t vb_ = dv + (uint64_t)((j % S) * ((Cfg::kVB * Cfg::kKVBox) >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+          umma_f16(tO + hh * 64, pb_ + (uint64_t)(2 * (2 * hh + kk)), vb_ + (uint64_t)(128 * (2 * hh + kk)), idesc_pv,
+                   (j | kk) ? 1u : 0u);
+        umma_commit(&pv_done[(2 * g + hh) * 2 + (j & 1)]);
+      };
+      mbar_wait(q_full, 0);
+      for (int j0 = 0; j0 < 2 && j0 < n; ++j0) {
+        mbar_wait(&k_full[j0 % S], (j0 / S) & 1);
+        tc_fence_after();
+        issue_qk(j0);
+      }
+      for (int j = 0; j < n; ++j) {
+        if (j + 2 < n) {
+          mbar_wait(&s_free[2 * g + (j & 1)], (j >> 1) & 1);
+          mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
+          tc_fence_after();
+          issue_qk(j + 2);
+        }
+        mbar_wait(&v_full[j % S], (j / S) & 1);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&p_full[(2 * g + hh) * 2 + (j & 1)], (j >> 1) & 1);
+          tc_fence_after();
+          issue_pv(j, hh);
+        }
+        umma_commit(&v_empty[j % S]);
+      }
+      umma_commit(&o_full[g]);
+    } else if (lane == 0 && n > 0) {
+      // tile 1 absent: nothing to issue, and k_empty / v_empty were initialised for a single committer
+    }
+  } else if (warp < 16) {
+    const int g = warp >> 3;
+    if (g == 0 || has1) {
+      const int h = (warp >> 2) & 1;
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+      const uint32_t tmem_O = tmem_base + 256 + (2 * g + h) * 64;     // this half's accumulator
+      const int pair_bar = 1 + g * 4 + quad;       // named barrier shared with the warp that owns the other 32 keys
+      float m_run = -INFINITY;
+      uint64_t* my_p_full = p_full + (2 * g + h) * 2;
+      uint64_t* my_pv_done = pv_done + (2 * g + h) * 2;
+      const int rows_tile = p.k_box1 * p.k_box2;   // keys a full tile holds (<= 64)
+      // 16-column chunks of O this half rescales / writes out
+      const int oc0 = h ? Cfg::kOChunks0 : 0, oc1 = h ? Cfg::kOChunks : Cfg::kOChunks0;
+      for (int j = 0; j < n; ++j) {
+        const int valid = ((j == n - 1) ? p.rows_k : rows_tile) - 32 * h;   // valid keys among this half's 32 columns
+        const int b = 2 * g + (j & 1);
+        mbar_wait(&s_full[b], (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t s[32];
+        tmem_ld32(tmem_base + lane_addr + b * 64 + 32 * h, s);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[b]);   // S buffer may be overwritten by QK^T(j+2)
+        if (valid < 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= valid) s[i] = 0xff800000u;    // absent key: score -inf -> P = 0
+        }
+        if (j == 0) {   // no stabiliser yet: this half's real row maximum first (a fully masked half gets a huge negative one)
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+          }
+          m_run = fmaxf(fmaxf(mx0, mx1) * p.scale_log2, -1.0e30f);
+        }
+        uint8_t* sPg = sP + b * Cfg::kPBox;
+        if (j >= 2) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);   // P columns of step j-2 consumed (long ago)
+#pragma unroll 1
+        for (int pass = 0;; ++pass) {
+          // Single pass with a STALE stabiliser (the running max of the previous steps); this step's max is accumulated in
+          // the same loop.  Only when a row's new max exceeds the stabiliser by more than kRescaleLog2 (P could overflow
+          // fp16) is the step redone with the updated stabiliser -- after the first few steps that never happens.
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          const float neg_m = -m_run;
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            uint4 q;
+            uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = c16 * 8 + 2 * t;
+              const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]);
+              if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
+              const bool poly = POLY == 1 ? (t == 1) : POLY == 2 ? (t & 1) : false;
+              const float y0 = fmaf(s0, p.scale_log2, neg_m), y1 = fmaf(s1, p.scale_log2, neg_m);
+              qw[t] = poly ? pack_f16x2(exp2_fma(y0), exp2_fma(y1)) : pack_f16x2(ex2_approx(y0), ex2_approx(y1));
+            }
+            *reinterpret_cast<uint4*>(sPg + sw128_offset(r, 4 * h + c16)) = q;
+          }
+          if (pass > 0 || j == 0) break;
+          const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
+          if (!__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) break;
+          // rare: O_g,h must be stable -> this half's PV of the previous step has to be complete
+          const float m_up = fmaxf(m_run, m_new);
+          mbar_wait(&my_pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          const float alpha = ex2_approx(m_run - m_up);
+#pragma unroll 1
+          for (int c = 0; c < Cfg::kOChunks; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_addr + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_addr + c * 16, o);
+          }
+          tmem_wait_st();
+          m_run = m_up;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&my_p_full[j & 1]);
+      }
+      // ---- epilogue: merge the two halves' partial softmax states; this half writes its chunks of the rows
+      mbar_wait(&o_full[g], 0);
+      tc_fence_after();
+      sMx[(g * 2 + h) * 128 + r] = m_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float m_oth = sMx[(g * 2 + (h ^ 1)) * 128 + r];
+      const float m_all = fmaxf(m_run, m_oth);
+      const float w_mine = ex2_approx(m_run - m_all), w_oth = ex2_approx(m_oth - m_all);
+      const float w0 = h ? w_oth : w_mine, w1 = h ? w_mine : w_oth;
+      const uint32_t tO0 = tmem_base + 256 + 2 * g * 64 + lane_addr, tO1 = tO0 + 64;
+      float inv;
+      {
+        uint32_t o0[16], o1[16];
+        tmem_ld16(tO0 + (D / 16) * 16, o0);
+        tmem_ld16(tO1 + (D / 16) * 16, o1);
+        tmem_wait_ld();
+        inv = p.out_scale / (w0 * __uint_as_float(o0[D % 16]) + w1 * __uint_as_float(o1[D % 16]));
+      }
+      const float a0 = w0 * inv, a1 = w1 * inv;
+      const int qt = qt0 + g;
+      const int q_i1 = (qt % p.q_t1) * p.q_box1, q_i2 = (qt / p.q_t1) * p.q_box2;
+      const bool row_ok = r < p.rows_q;
+      const int i1 = q_i1 + r % p.q_box1;
+      const int i2 = q_i2 + r / p.q_box1;
+      __half* orow = p.out + (int64_t)i1 * p.os1 + (int64_t)i2 * p.os2 + (int64_t)q_i3 * p.os3 + (int64_t)q_i4 * p.os4 + head * D;
+#pragma unroll 1
+      for (int c = oc0; c < oc1; ++c) {
+        if (c * 16 >= D) break;
+        uint32_t o[16], o1[16];
+        tmem_ld16(tO0 + c * 16, o);
+        tmem_ld16(tO1 + c * 16, o1);
+        tmem_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            if (c * 16 + gq * 8 < D) {
+              uint4 q;
+              __half2* hh = reinterpret_cast<__half2*>(&q);
+              float v[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[t] = a0 * __uint_as_float(o[gq * 8 + t]) + a1 * __uint_as_float(o1[gq * 8 + t]);
+              if (p.accumulate) {
+                const uint4 old = *reinterpret_cast<const uint4*>(orow + c * 16 + gq * 8);
+                const __half2* ho = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __half22float2(ho[t]);
+                  v[2 * t] += f.x;
+                  v[2 * t + 1] += f.y;
+                }
+              }
+#pragma unroll
+              for (int t = 0; t < 4; ++t) hh[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+              *reinterpret_cast<uint4*>(orow + c * 16 + gq * 8) = q;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 19) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // SIMT bring-up / reference kernel (one thread per (batch, head, query)); same view semantics, fp32 math
 // ---------------------------------------------------------------------------------------------------------------
 struct ViewDev {
@@ -1597,6 +1951,27 @@ static int launch_attn3(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
 }
 
 template <int D, int POLY>
+static int launch_attn5(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
+  using Cfg = Attn5Cfg<D>;
+  int kb1, kb2, kt1, ktiles, klast;
+  if (int r = tile_geom_k64(a->k, &kb1, &kb2, &kt1, &ktiles, &klast)) return r;
+  dev.kv_tiles = ktiles; dev.rows_k = klast; dev.k_t1 = kt1; dev.k_box1 = kb1; dev.k_box2 = kb2;
+  dev.k_box_bytes = 128u * (uint32_t)(kb1 * kb2);
+  const CUtensorMap *mk, *mv;
+  if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
+  if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
+  static bool attr_set = false;
+  if (!attr_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn5_tc_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  grid.x = (grid.x + 1) / 2;
+  attn5_tc_kernel<D, POLY><<<grid, 640, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+template <int D, int POLY>
 static int launch_attn4(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
   using Cfg = Attn4Cfg<D>;
   int kb1, kb2, kt1, ktiles, klast;
@@ -1623,7 +1998,7 @@ static int attn_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("A3D_ATTN_VARIANT");
-    v = e ? atoi(e) : 4;
+    v = e ? atoi(e) : 5;
   }
   return v;
 }
@@ -1715,9 +2090,9 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
       if (attn_variant() == 1) return launch_attn<40>(dev, mq, mk, mv, grid, st);
       if (attn_variant() == 2) return launch_attn2<40>(dev, mq, mk, mv, grid, st);
       if (attn_variant() == 3) return launch_attn3<40>(dev, a, mq, grid, st);
-      if (attn_mode() == 1) return launch_attn4<40, 1>(dev, a, mq, grid, st);
-      if (attn_mode() == 2) return launch_attn4<40, 2>(dev, a, mq, grid, st);
-      return launch_attn4<40, 0>(dev, a, mq, grid, st);
+      if (attn_variant() == 4) return launch_attn4<40, 0>(dev, a, mq, grid, st);
+      if (attn_mode() == 1) return launch_attn5<40, 1>(dev, a, mq, grid, st);
+      return launch_attn5<40, 0>(dev, a, mq, grid, st);
     case 80:
       if (attn_variant() >= 4 && attn_variant80()) return launch_attn4<80, 0>(dev, a, mq, grid, st);
       return launch_attn<80>(dev, mq, mk, mv, grid, st);

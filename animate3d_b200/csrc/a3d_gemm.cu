@@ -29,6 +29,9 @@ struct GemmDev {
   const float* bias;
   const float* rowbias;
   int64_t rb_ld, rb_div, rb_mod;
+  int rb_stage;   // row-bias table rows a 128-row tile touches are staged in shared memory: 0 = no (global loads),
+                  // 1 = slot = row_in_tile / rb_div (rb_div >= 8 divides 128, or rb_div % 128 == 0), 2 = slot = row_in_tile % rb_mod
+  int rb_slots;   // distinct table rows per tile (<= 16)
   float acc_scale;
   const __half* R1; int64_t ldr1; float r1_scale;
   const __half* R2; int64_t ldr2;
@@ -68,7 +71,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStageOut = 2048;   // 2 x 256 fp32 bias values (double-buffered with the accumulator)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kRbLd = BN + 8;      // padded row of the staged row-bias slice (staggers the banks of the <=16 slots)
+  static constexpr int kRbBytes = 16 * kRbLd * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + kRbBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 // EPI: 0 = bias/row-bias only, 1 = + residuals / row permutation, 2 = GEGLU, 3 = fp32 output (register pressure and dead
@@ -84,7 +90,8 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStageOut);
+  float* smem_rb = reinterpret_cast<float*>(smem_stage + Cfg::kStageOut);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStageOut + Cfg::kRbBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -193,11 +200,33 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       const int64_t n_out = (EPI == kEpiGeglu) ? p.N / 2 : p.N;
       // the tile's BN bias values: one coalesced load by the 256 epilogue threads, then broadcast reads from shared memory
       float* sb = reinterpret_cast<float*>(smem_stage) + acc * 256;
+      // Row-bias (positional-encoding / time-embedding tables, fp32 [table rows, N]): a 128-row tile touches at most 16
+      // distinct table rows.  Staged once per tile with coalesced loads instead of 128 x BN scattered 4-byte L2 reads (the
+      // K=320 QKV projections with a table were 2x slower than the plain ones).  Single buffer: the barrier in front keeps
+      // a fast warp from overwriting slots a slow warp still reads for the previous tile.
+      const float* rbs = nullptr;
+      if (p.rb_stage) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int64_t tile_row0 = (int64_t)mt * kBM;
+        constexpr int kVec = BN / 4;
+        for (int i = threadIdx.x; i < p.rb_slots * kVec; i += 256) {
+          const int slot = i / kVec, c4 = i % kVec;
+          const int64_t rep = tile_row0 + (p.rb_stage == 1 ? (int64_t)slot * p.rb_div : (int64_t)slot);
+          const int64_t trow = (rep / p.rb_div) % p.rb_mod;
+          const int64_t col = (int64_t)nt * BN + c4 * 4;
+          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col + 4 <= p.N && rep < p.M) v4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + trow * p.rb_ld + col));
+          *reinterpret_cast<float4*>(smem_rb + slot * Cfg::kRbLd + c4 * 4) = v4;
+        }
+        const int rit = quad * 32 + lane;
+        const int slot = p.rb_stage == 1 ? (int)(rit / p.rb_div) : (int)(rit % p.rb_mod);
+        rbs = smem_rb + slot * Cfg::kRbLd;
+      }
       if (p.bias) {
         const int64_t bc = (int64_t)nt * BN + threadIdx.x;
         if (threadIdx.x < BN) sb[threadIdx.x] = bc < p.N ? __ldg(p.bias + bc) : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      if (p.bias || p.rb_stage) asm volatile("bar.sync 1, 256;" ::: "memory");
 
       // fp32 values of 32 accumulator columns -> + bias + rowbias, * scale
       auto finish32 = [&](uint32_t* r, int64_t col0) {
@@ -211,7 +240,14 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
               v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
-          if (p.rowbias) {
+          if (rbs) {
+            const float4* rb = reinterpret_cast<const float4*>(rbs + (col0 - (int64_t)nt * BN));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = rb[i];
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          } else if (p.rowbias) {
             const float4* rb = reinterpret_cast<const float4*>(p.rowbias + rbrow * p.rb_ld + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -497,6 +533,12 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   d.tiles_n = (int)((a->N + BN - 1) / BN);
   d.cpb = a->a_mode == A3D_A_CONV3 ? cv.c / kBK : 0;
   d.tpi = tpi; d.boh = boh; d.bimg = bimg;
+  d.rb_stage = 0; d.rb_slots = 0;
+  if (a->rowbias && (a->N % 4 == 0) && (a->rb_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->rowbias) & 15) == 0)) {
+    if (d.rb_div % kBM == 0) { d.rb_stage = 1; d.rb_slots = 1; }                                  // one table row per tile
+    else if (d.rb_div >= 8 && kBM % d.rb_div == 0) { d.rb_stage = 1; d.rb_slots = (int)(kBM / d.rb_div); }
+    else if (d.rb_div == 1 && d.rb_mod <= 16 && kBM % d.rb_mod == 0) { d.rb_stage = 2; d.rb_slots = (int)d.rb_mod; }
+  }
 
   const CUtensorMap *mapA = nullptr, *mapB = nullptr;
   {
