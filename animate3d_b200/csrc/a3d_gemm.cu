@@ -525,8 +525,17 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   int BN;
   if (a->geglu) BN = (a->N % 256 == 0) ? 256 : 128;
   else if (a->N % 256 == 0) BN = 256;
-  else if (a->N % 160 == 0) BN = 160;
+  else if (a->K <= 640 && a->N > 512 && (256 * ((a->N + 255) / 256) - a->N) * 8 <= a->N) {
+    // short-K GEMMs are bound by the epilogue / output stores, where the 256-wide tile amortises the per-tile handshakes
+    // best: a ragged last tile (<= 12.5% idle MMA columns) costs nothing there
+    BN = 256;
+  } else if (a->N % 160 == 0) BN = 160;
   else BN = 128;
+  {
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("A3D_GEMM_BN"); force = e ? atoi(e) : 0; }
+    if (!a->geglu && (force == 128 || force == 160 || force == 256)) BN = force;   // tuning override
+  }
   if (a->geglu && a->N % BN) return fail(A3D_EINVAL, "a3d_gemm: GEGLU needs N %% 128 == 0");
   d.num_k_blocks = (int)(a->K / kBK);
   d.tiles_m = (int)((a->M + kBM - 1) / kBM);

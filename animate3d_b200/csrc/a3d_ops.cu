@@ -16,91 +16,138 @@ __device__ __forceinline__ int64_t perm_row2(int64_t m, int64_t a, int64_t b) {
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// stats: grid (chunks, samples); block = C/8 threads (one uint4 = 8 channels per thread), loops over the chunk's rows.
-__global__ void gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
-                                int64_t rows_per_sample, int rows_per_chunk, int groups, float* __restrict__ stats) {
+// Both passes: grid (row chunks, samples); a thread owns one 8-channel vector column (fixed for its lifetime, so gamma / beta /
+// group statistics are folded into per-thread scale/shift registers once) and walks rows r0 + rsub, + rows_par, ...;
+// blockDim = rows_par * (C / 8).  Four independent 16-byte loads in flight per thread.
+// rows per block (chunk) is chosen on the host: 128 when that still yields >= ~4 blocks per SM, fewer rows otherwise (the
+// over-frames GroupNorm of the motion modules has only B*Nv = 8 samples)
+
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int rows_per_sample, int groups,
+                int rows_par, int chunk_rows, float* __restrict__ stats) {
   extern __shared__ float sm[];  // [2 * groups]
   const int C = c1 + c2;
+  const int vpr = C / 8;
   const int cpg = C / groups;
   const int sample = blockIdx.y;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
-  int64_t r1 = r0 + rows_per_chunk;
-  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  const int r0 = blockIdx.x * chunk_rows;
+  const int r1 = min(r0 + chunk_rows, rows_per_sample);
   for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  const int c0 = threadIdx.x * 8;
-  if (c0 < C) {
-    const __half* src = (c0 < c1) ? x1 : x2;
-    const int cc = (c0 < c1) ? c0 : c0 - c1;
-    const int ld = (c0 < c1) ? c1 : c2;
+  const int vec = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
+  if (rsub < rows_par) {
+    const int c0 = vec * 8;
+    const bool first = c0 < c1;
+    const int ld = first ? c1 : c2;
+    const __half* src = (first ? x1 + c0 : x2 + (c0 - c1)) + (int64_t)sample * rows_per_sample * ld;
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    for (int64_t r = r0; r < r1; ++r) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)sample * rows_per_sample + r) * ld + cc));
+    auto add = [&](const uint4& v) {
       const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(h[i]);
-        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
-        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+        s[2 * i] += f.x; q[2 * i] = fmaf(f.x, f.x, q[2 * i]);
+        s[2 * i + 1] += f.y; q[2 * i + 1] = fmaf(f.y, f.y, q[2 * i + 1]);
       }
+    };
+    int r = r0 + rsub;
+    for (; r + 3 * rows_par < r1; r += 4 * rows_par) {
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld));
+      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(r + rows_par) * ld));
+      const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(r + 2 * rows_par) * ld));
+      const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(r + 3 * rows_par) * ld));
+      add(v0); add(v1); add(v2); add(v3);
     }
+    for (; r < r1; r += rows_par) add(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld)));
+    // the 8 channels of a vector span at most two groups (cpg >= 8)
+    const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;
+    const int split = (g0 + 1) * cpg - c0;
+    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int g = (c0 + i) / cpg;
-      atomicAdd(&sm[2 * g], s[i]);
-      atomicAdd(&sm[2 * g + 1], q[i]);
+      if (i < split) { sa += s[i]; qa += q[i]; } else { sb += s[i]; qb += q[i]; }
+    }
+    atomicAdd(&sm[2 * g0], sa);
+    atomicAdd(&sm[2 * g0 + 1], qa);
+    if (g1 != g0) {
+      atomicAdd(&sm[2 * g1], sb);
+      atomicAdd(&sm[2 * g1 + 1], qb);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(int64_t)sample * 2 * groups + i], sm[i]);
 }
 
-__global__ void gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
-                                int64_t total_rows, int64_t rows_per_sample, int groups, float eps, int silu,
-                                int64_t perm_a, int64_t perm_b, const float* __restrict__ stats) {
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __half* __restrict__ y, int rows_per_sample, int groups, float eps, int silu,
+                int64_t perm_a, int64_t perm_b, int rows_par, int chunk_rows, const float* __restrict__ stats) {
   const int C = c1 + c2;
-  const int cpg = C / groups;                 // >= 8: the 8 channels of a thread span at most two groups
-  const int vec_per_row = C / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total_rows * vec_per_row) return;
-  const int64_t row = idx / vec_per_row;
-  const int c0 = (int)(idx % vec_per_row) * 8;
-  const int64_t sample = row / rows_per_sample;
-  const float inv_n = 1.0f / (float)(rows_per_sample * cpg);
-  const __half* src = (c0 < c1) ? x1 + row * c1 + c0 : x2 + row * c2 + (c0 - c1);
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-  const int g0 = c0 / cpg;
-  const int g1 = (c0 + 7) / cpg;
-  const int split = (g0 + 1) * cpg - c0;      // first channel (0..8) that belongs to g1
-  const float2 sa = *reinterpret_cast<const float2*>(stats + (sample * groups + g0) * 2);
-  const float2 sb = *reinterpret_cast<const float2*>(stats + (sample * groups + g1) * 2);
-  const float mean0 = sa.x * inv_n, mean1 = sb.x * inv_n;
-  const float rstd0 = rsqrtf(fmaxf(sa.y * inv_n - mean0 * mean0, 0.f) + eps);
-  const float rstd1 = rsqrtf(fmaxf(sb.y * inv_n - mean1 * mean1, 0.f) + eps);
-  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
-  const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0)), bb = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
-  const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-  const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-  const __half2* h = reinterpret_cast<const __half2*>(&v);
-  float r[8];
+  const int vpr = C / 8;
+  const int cpg = C / groups;
+  const int sample = blockIdx.y;
+  const int r0 = blockIdx.x * chunk_rows;
+  const int r1 = min(r0 + chunk_rows, rows_per_sample);
+  const int vec = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
+  if (rsub >= rows_par) return;
+  const int c0 = vec * 8;
+  const bool first = c0 < c1;
+  const int ld = first ? c1 : c2;
+  const int64_t row_base = (int64_t)sample * rows_per_sample;
+  const __half* src = (first ? x1 + c0 : x2 + (c0 - c1)) + row_base * ld;
+  // y = x * scale + shift with scale = rstd * gamma, shift = beta - mean * rstd * gamma
+  float scale[8], shift[8];
+  {
+    const float inv_n = 1.0f / ((float)rows_per_sample * (float)cpg);
+    const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;
+    const int split = (g0 + 1) * cpg - c0;
+    const float2 sa = *reinterpret_cast<const float2*>(stats + ((int64_t)sample * groups + g0) * 2);
+    const float2 sb = *reinterpret_cast<const float2*>(stats + ((int64_t)sample * groups + g1) * 2);
+    const float mean0 = sa.x * inv_n, mean1 = sb.x * inv_n;
+    const float rstd0 = rsqrtf(fmaxf(sa.y * inv_n - mean0 * mean0, 0.f) + eps);
+    const float rstd1 = rsqrtf(fmaxf(sb.y * inv_n - mean1 * mean1, 0.f) + eps);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0)), bb = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+    const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); r[2 * i] = f.x; r[2 * i + 1] = f.y; }
-  uint4 o;
-  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool second = i >= split;
-    float t = (r[i] - (second ? mean1 : mean0)) * (second ? rstd1 : rstd0) * gg[i] + be[i];
-    if (silu) t = silu_f(t);
-    r[i] = t;
+    for (int i = 0; i < 8; ++i) {
+      const bool second = i >= split;
+      scale[i] = (second ? rstd1 : rstd0) * gg[i];
+      shift[i] = be[i] - (second ? mean1 : mean0) * scale[i];
+    }
   }
+  auto emit = [&](const uint4& v, int r) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    float t[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) ow[i] = pack_f16x2(r[2 * i], r[2 * i + 1]);
-  const int64_t orow = perm_row2(row, perm_a, perm_b);
-  *reinterpret_cast<uint4*>(y + orow * C + c0) = o;
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      t[2 * i] = fmaf(f.x, scale[2 * i], shift[2 * i]);
+      t[2 * i + 1] = fmaf(f.y, scale[2 * i + 1], shift[2 * i + 1]);
+    }
+    if (silu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = silu_f(t[i]);
+    }
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ow[i] = pack_f16x2(t[2 * i], t[2 * i + 1]);
+    const int64_t orow = perm_row2(row_base + r, perm_a, perm_b);
+    *reinterpret_cast<uint4*>(y + orow * C + c0) = o;
+  };
+  int r = r0 + rsub;
+  for (; r + 3 * rows_par < r1; r += 4 * rows_par) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld));
+    const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(r + rows_par) * ld));
+    const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(r + 2 * rows_par) * ld));
+    const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(r + 3 * rows_par) * ld));
+    emit(v0, r); emit(v1, r + rows_par); emit(v2, r + 2 * rows_par); emit(v3, r + 3 * rows_par);
+  }
+  for (; r < r1; r += rows_par) emit(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld)), r);
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
@@ -251,6 +298,110 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
 #pragma unroll
     for (int t = 0; t < 4; ++t) ow[t] = pack_f16x2(acc[2 * t] * inv, acc[2 * t + 1] * inv);
     *reinterpret_cast<uint4*>(o + c * 8) = ov;
+  }
+}
+
+// F == 16 (the shipped motion modules): one block per pixel, one warp per head, the whole 16 x 16 attention of a head as
+// mma.sync.m16n8k16 tiles (a 16-frame problem is far below a tcgen05 tile; the legacy warp-level MMA is the right size).
+// The pixel's [16 frames, 3C] slab is staged in shared memory with coalesced 16-byte loads (rows padded by 16 B so the
+// fragment loads of the 8 row groups hit different banks); S and P never leave registers (the accumulator fragment of QK^T
+// is exactly the A fragment of P V); the normalised O goes back over the head's dead Q slice and leaves with coalesced
+// 16-byte stores.  ~100 warp instructions per (pixel, head) instead of ~1500 in the scalar kernel: HBM-bound.
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int heads,
+                                                             float scale_log2) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int C = heads * D;
+  const int ld = 3 * C + 8;                    // padded row (halves)
+  __half* sm = reinterpret_cast<__half*>(smraw);
+  const int64_t pix = blockIdx.x;
+  const __half* base = qkv + pix * 16 * 3 * C;
+  const int vec_row = 3 * C / 8;
+  for (int i = threadIdx.x; i < 16 * vec_row; i += blockDim.x) {
+    const int f = i / vec_row, v = i % vec_row;
+    *reinterpret_cast<uint4*>(sm + f * ld + v * 8) = __ldg(reinterpret_cast<const uint4*>(base) + i);
+  }
+  __syncthreads();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  if (h < heads) {
+    const __half* q = sm + h * D;
+    const __half* k = sm + C + h * D;
+    const __half* v = sm + 2 * C + h * D;
+    // ---- S = Q K^T: two 8-key n-tiles, ceil(D / 16) k-steps (the last one half empty when D % 16 == 8)
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int KS = (D + 15) / 16;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      const int d0 = kk * 16 + 2 * t;
+      const bool hi_ok = (kk * 16 + 8) < D;    // second 8-column half of this k-step inside the head?
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(q + g * ld + d0);
+      a[1] = *reinterpret_cast<const uint32_t*>(q + (g + 8) * ld + d0);
+      a[2] = hi_ok ? *reinterpret_cast<const uint32_t*>(q + g * ld + d0 + 8) : 0u;
+      a[3] = hi_ok ? *reinterpret_cast<const uint32_t*>(q + (g + 8) * ld + d0 + 8) : 0u;
+      const uint32_t b00 = *reinterpret_cast<const uint32_t*>(k + g * ld + d0);
+      const uint32_t b01 = hi_ok ? *reinterpret_cast<const uint32_t*>(k + g * ld + d0 + 8) : 0u;
+      const uint32_t b10 = *reinterpret_cast<const uint32_t*>(k + (g + 8) * ld + d0);
+      const uint32_t b11 = hi_ok ? *reinterpret_cast<const uint32_t*>(k + (g + 8) * ld + d0 + 8) : 0u;
+      mma_16816(s0, a, b00, b01);
+      mma_16816(s1, a, b10, b11);
+    }
+    // ---- softmax over the 16 keys of rows g (c0,c1) and g+8 (c2,c3); a row lives in the 4 lanes of a quad
+    float mx_lo = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+    float mx_hi = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o));
+      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, o));
+    }
+    const float nl = -mx_lo * scale_log2, nh = -mx_hi * scale_log2;
+    float p0[4], p1[4];
+    p0[0] = ex2_approx(fmaf(s0[0], scale_log2, nl)); p0[1] = ex2_approx(fmaf(s0[1], scale_log2, nl));
+    p0[2] = ex2_approx(fmaf(s0[2], scale_log2, nh)); p0[3] = ex2_approx(fmaf(s0[3], scale_log2, nh));
+    p1[0] = ex2_approx(fmaf(s1[0], scale_log2, nl)); p1[1] = ex2_approx(fmaf(s1[1], scale_log2, nl));
+    p1[2] = ex2_approx(fmaf(s1[2], scale_log2, nh)); p1[3] = ex2_approx(fmaf(s1[3], scale_log2, nh));
+    float sum_lo = p0[0] + p0[1] + p1[0] + p1[1], sum_hi = p0[2] + p0[3] + p1[2] + p1[3];
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, o);
+      sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, o);
+    }
+    const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+    // P as the A fragment of the PV product (normalised first: fp16 P in [0,1])
+    uint32_t pa[4];
+    pa[0] = pack_f16x2(p0[0] * inv_lo, p0[1] * inv_lo);
+    pa[1] = pack_f16x2(p0[2] * inv_hi, p0[3] * inv_hi);
+    pa[2] = pack_f16x2(p1[0] * inv_lo, p1[1] * inv_lo);
+    pa[3] = pack_f16x2(p1[2] * inv_hi, p1[3] * inv_hi);
+    // ---- O = P V, 8 value columns per n-tile; V^T fragments through ldmatrix.trans (rows = key frames)
+    __syncwarp();
+    __half* orow_lo = sm + g * ld + h * D;          // the head's Q slice is dead now: O overwrites it
+    __half* orow_hi = sm + (g + 8) * ld + h * D;
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt) {
+      // lanes 0..15 supply the row addresses of the two 8x8 blocks (keys 0-7, keys 8-15) of columns nt*8 .. nt*8+7
+      const uint32_t addr = smem_u32(v + (lane & 15) * ld + nt * 8);
+      uint32_t b0, b1;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_16816(o, pa, b0, b1);
+      *reinterpret_cast<uint32_t*>(orow_lo + nt * 8 + 2 * t) = pack_f16x2(o[0], o[1]);
+      *reinterpret_cast<uint32_t*>(orow_hi + nt * 8 + 2 * t) = pack_f16x2(o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  const int ovec = C / 8;
+  __half* obase = out + pix * 16 * C;
+  for (int i = threadIdx.x; i < 16 * ovec; i += blockDim.x) {
+    const int f = i / ovec, vv = i % ovec;
+    reinterpret_cast<uint4*>(obase)[i] = *reinterpret_cast<const uint4*>(sm + f * ld + vv * 8);
   }
 }
 
@@ -407,18 +558,23 @@ extern "C" int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, co
   if (!x2) c2 = 0;
   if (C % groups || C % 8 || c1 % 8 || c2 % 8 || C / 8 > 1024 || groups > 64)
     return fail(A3D_EINVAL, "a3d_group_norm: unsupported channels C=%d (c1=%d c2=%d) groups=%d", C, c1, c2, groups);
+  if (rows_per_sample > (int64_t)1 << 30 || samples > 65535) return fail(A3D_EINVAL, "a3d_group_norm: extent too large");
   A3D_CUDA_CHECK(cudaMemsetAsync(ws_stats, 0, sizeof(float) * 2 * groups * samples, st));
-  const int rows_per_chunk = 64;
-  dim3 grid((unsigned)((rows_per_sample + rows_per_chunk - 1) / rows_per_chunk), (unsigned)samples);
-  const int threads = ((C / 8 + 31) / 32) * 32;
+  const int vpr = C / 8;
+  int rows_par = 256 / vpr;
+  if (rows_par < 1) rows_par = 1;
+  const int threads = ((rows_par * vpr + 31) / 32) * 32;   // <= 256 (C / 8 <= 160 for the UNet's widths) or one row per block
+  if (threads > 512) return fail(A3D_EINVAL, "a3d_group_norm: C=%d too wide", C);
+  int chunk_rows = 128;
+  while (chunk_rows > 4 * rows_par && ((rows_per_sample + chunk_rows - 1) / chunk_rows) * samples < 592) chunk_rows /= 2;
+  dim3 grid((unsigned)((rows_per_sample + chunk_rows - 1) / chunk_rows), (unsigned)samples);
   gn_stats_kernel<<<grid, threads, 2 * groups * sizeof(float), st>>>(reinterpret_cast<const __half*>(x1), c1,
-                                                                     reinterpret_cast<const __half*>(x2), c2, rows_per_sample,
-                                                                     rows_per_chunk, groups, ws_stats);
+                                                                     reinterpret_cast<const __half*>(x2), c2,
+                                                                     (int)rows_per_sample, groups, rows_par, chunk_rows, ws_stats);
   A3D_LAUNCH_CHECK();
-  const int64_t total = samples * rows_per_sample * (C / 8);
-  gn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const __half*>(x1), c1, reinterpret_cast<const __half*>(x2), c2, gamma, beta,
-      reinterpret_cast<__half*>(y), samples * rows_per_sample, rows_per_sample, groups, eps, silu, perm_a, perm_b, ws_stats);
+  gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __half*>(x1), c1, reinterpret_cast<const __half*>(x2), c2,
+                                            gamma, beta, reinterpret_cast<__half*>(y), (int)rows_per_sample, groups, eps, silu,
+                                            perm_a, perm_b, rows_par, chunk_rows, ws_stats);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
@@ -445,6 +601,18 @@ extern "C" int a3d_layer_norm(const void* x, const float* gamma, const float* be
 
 template <int D>
 static int launch_temporal(const void* qkv, void* out, int64_t pixels, int frames, int heads, float scale, cudaStream_t st) {
+  if (frames == 16 && heads <= 8) {
+    const size_t smem16 = (size_t)16 * (3 * heads * D + 8) * 2;
+    static size_t max_set16 = 0;
+    if (smem16 > 48 * 1024 && smem16 > max_set16) {
+      A3D_CUDA_CHECK(cudaFuncSetAttribute(temporal_attn16_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+      max_set16 = smem16;
+    }
+    temporal_attn16_kernel<D><<<(unsigned)pixels, heads * 32, smem16, st>>>(
+        reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), heads, scale * 1.4426950408889634f);
+    A3D_LAUNCH_CHECK();
+    return A3D_OK;
+  }
   const size_t smem = (size_t)frames * 2 * heads * D * 2;
   static size_t max_set = 0;
   if (smem > 48 * 1024 && smem > max_set) {
