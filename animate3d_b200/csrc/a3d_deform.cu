@@ -2,7 +2,10 @@
 //   k-planes (HexPlane) lookup -- 2 scales x 6 planes, bilinear, border clamp, align_corners -- product over planes, concat
 //   over scales -> 32 features -> three bias-free MLPs 32 -> 32 (ReLU) -> {3, 4, 3} -> xyz + d, exp(s + d), normalize(q + d)
 // forward and backward (gradients to the plane grids and MLP weights; the static gaussians are frozen buffers in
-// Animate3D, gaussian_4d.py:262-297).  Replaces, per (frame, gaussian), the 12 grid_sample + 6 GEMM + elementwise launches the
+// Animate3D, gaussian_4d.py:262-297).  The `use_global_trans` branch (gaussian_4d.py:499-511, 525-539) needs the MEAN feature
+// vector of a frame before any output can be formed: kMode 2 computes those means (one extra pass over the L2-resident
+// planes), the host evaluates the two 32-wide global MLPs + Euler matrix on [T, 32], and the main pass takes the rotated
+// base quaternions as `rot_base`; backward returns d/d rot_base and folds d/d mean-feature back into the plane gradients.  Replaces, per (frame, gaussian), the 12 grid_sample + 6 GEMM + elementwise launches the
 // reference issues PER CAMERA (custom/threestudio-animate3d/geometry/gaussian_4d.py:39-64, 450-548;
 // renderer/diff_gaussian_rasterizer_advanced_4d.py:77-83, 119-135) and de-duplicates the 4 views of a frame.
 #include "a3d_host.cuh"
@@ -46,12 +49,21 @@ __device__ __forceinline__ Bilerp bilerp_setup(float gx, float gy, int W, int H)
   return b;
 }
 
-template <bool kBackward>
+struct DeformGlobal {
+  const float* rot_base;      // [T,P,4] per-frame base quaternions (replace `rotation`) or null
+  float* g_rot_base;          // backward: d/d rot_base, [T,P,4], or null
+  const float* g_featmean;    // backward: d/d (mean feature of frame t), [T, nfeat], or null
+  float* featmean;            // kMode 2: [T, nfeat], pre-zeroed; receives sum / P
+};
+
+// kMode: 0 = forward, 1 = backward, 2 = per-frame mean of the k-planes features only
+template <int kMode>
 __global__ void __launch_bounds__(128)
-deform_kernel(DeformGrids G, DeformMlp M, const float* __restrict__ xyz, const float* __restrict__ scaling,
+deform_kernel(DeformGrids G, DeformMlp M, DeformGlobal X, const float* __restrict__ xyz, const float* __restrict__ scaling,
               const float* __restrict__ rotation, const float* __restrict__ times, int P, int T, int deform_scale,
               float* __restrict__ out_means, float* __restrict__ out_scales, float* __restrict__ out_rots,
               const float* __restrict__ g_means, const float* __restrict__ g_scales, const float* __restrict__ g_rots) {
+  constexpr bool kBackward = kMode == 1;
   extern __shared__ float sm[];
   // shared copies of the MLP weights (and, in backward, of their gradient accumulators)
   float* sw1 = sm;                                   // [3][32][32]
@@ -59,15 +71,19 @@ deform_kernel(DeformGrids G, DeformMlp M, const float* __restrict__ xyz, const f
   float* sg1 = sw2 + 3 * 4 * kHid;                   // backward only
   float* sg2 = sg1 + 3 * kHid * kHid;
   const int nfeat = G.scales * kFeat;
-  for (int i = threadIdx.x; i < 3 * kHid * kHid; i += blockDim.x) {
-    const int m = i / (kHid * kHid), r = i % (kHid * kHid);
-    sw1[i] = (r % kHid < nfeat) ? M.w1[m][(r / kHid) * nfeat + r % kHid] : 0.f;
-    if (kBackward) sg1[i] = 0.f;
-  }
-  for (int i = threadIdx.x; i < 3 * 4 * kHid; i += blockDim.x) {
-    const int m = i / (4 * kHid), r = (i % (4 * kHid)) / kHid, c = i % kHid;
-    sw2[i] = r < out_dim(m) ? M.w2[m][r * kHid + c] : 0.f;
-    if (kBackward) sg2[i] = 0.f;
+  if (kMode != 2) {
+    for (int i = threadIdx.x; i < 3 * kHid * kHid; i += blockDim.x) {
+      const int m = i / (kHid * kHid), r = i % (kHid * kHid);
+      sw1[i] = (r % kHid < nfeat) ? M.w1[m][(r / kHid) * nfeat + r % kHid] : 0.f;
+      if (kBackward) sg1[i] = 0.f;
+    }
+    for (int i = threadIdx.x; i < 3 * 4 * kHid; i += blockDim.x) {
+      const int m = i / (4 * kHid), r = (i % (4 * kHid)) / kHid, c = i % kHid;
+      sw2[i] = r < out_dim(m) ? M.w2[m][r * kHid + c] : 0.f;
+      if (kBackward) sg2[i] = 0.f;
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * kHid; i += blockDim.x) sm[i] = 0.f;   // [2 frames a block may straddle][32]
   }
   __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +111,26 @@ deform_kernel(DeformGrids G, DeformMlp M, const float* __restrict__ xyz, const f
         }
       }
   }
+  if (kMode == 2) {
+    // block-level sum per frame (a 128-thread block touches at most two frames when P >= 128), then one atomic per value
+    const int t_first = (blockIdx.x * blockDim.x) / P;
+    if (active) {
+      const int slot = t - t_first;
+      if (slot < 2) {
+#pragma unroll
+        for (int c = 0; c < kHid; ++c) if (c < nfeat) atomicAdd(&sm[slot * kHid + c], feat[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < kHid; ++c) if (c < nfeat) atomicAdd(&X.featmean[(size_t)t * nfeat + c], feat[c] / (float)P);
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * kHid; k += blockDim.x) {
+      const int slot = k / kHid, c = k % kHid;
+      if (c < nfeat && t_first + slot < T && sm[k] != 0.f) atomicAdd(&X.featmean[(size_t)(t_first + slot) * nfeat + c], sm[k] / (float)P);
+    }
+    return;
+  }
   // ---- three MLPs
   float hid[3][kHid];
   float outv[3][4];
@@ -118,7 +154,8 @@ deform_kernel(DeformGrids G, DeformMlp M, const float* __restrict__ xyz, const f
   float q[4] = {0.f, 0.f, 0.f, 1.f}, sc[3] = {0.f, 0.f, 0.f};
   float qn = 1.f;
   if (active) {
-    for (int k = 0; k < 4; ++k) q[k] = rotation[4 * i + k] + outv[1][k];
+    const float* qb = X.rot_base ? X.rot_base + 4 * ((size_t)t * P + i) : rotation + 4 * i;
+    for (int k = 0; k < 4; ++k) q[k] = qb[k] + outv[1][k];
     qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
     for (int k = 0; k < 3; ++k) sc[k] = expf(scaling[3 * i + k] + (deform_scale ? outv[2][k] : 0.f));
   }
@@ -146,6 +183,7 @@ deform_kernel(DeformGrids G, DeformMlp M, const float* __restrict__ xyz, const f
       for (int k = 0; k < 4; ++k) { y[k] = q[k] / qn; dot += y[k] * g_rots[4 * o + k]; }
       for (int k = 0; k < 4; ++k) dout[1][k] = (g_rots[4 * o + k] - y[k] * dot) / qn;
     }
+    if (X.g_rot_base) for (int k = 0; k < 4; ++k) X.g_rot_base[4 * o + k] = dout[1][k];   // q = rot_base + delta
   }
   float dfeat[kHid];
 #pragma unroll
@@ -184,6 +222,10 @@ deform_kernel(DeformGrids G, DeformMlp M, const float* __restrict__ xyz, const f
       for (int r = 0; r < kHid; ++r) a = fmaf(sw1[(m * kHid + r) * kHid + c], dh[r], a);
       dfeat[c] += a;
     }
+  }
+  if (active && X.g_featmean) {
+#pragma unroll
+    for (int c = 0; c < kHid; ++c) if (c < nfeat) dfeat[c] += X.g_featmean[(size_t)t * nfeat + c] / (float)P;
   }
   if (active) {
     // d sample_p = dfeat * prod_{q != p} sample_q = dfeat * feat / sample_p  (recompute samples; guard tiny values)
@@ -231,6 +273,12 @@ deform_kernel(DeformGrids G, DeformMlp M, const float* __restrict__ xyz, const f
 
 using namespace a3d;
 
+static DeformGlobal globals(const a3d_deform_args* a, float* featmean) {
+  DeformGlobal X;
+  X.rot_base = a->rot_base; X.g_rot_base = a->grad_rot_base; X.g_featmean = a->grad_featmean; X.featmean = featmean;
+  return X;
+}
+
 static int fill(const a3d_deform_args* a, DeformGrids* G, DeformMlp* M) {
   const bool bwd = a && a->grad_w1[0] != nullptr;
   (void)bwd;
@@ -264,8 +312,23 @@ extern "C" int a3d_deform_forward(const a3d_deform_args* a, float* means, float*
   if (int r = fill(a, &G, &M)) return r;
   const int n = a->P * a->T;
   const size_t smem = (3 * kHid * kHid + 3 * 4 * kHid) * sizeof(float);
-  deform_kernel<false><<<(n + 127) / 128, 128, smem, st>>>(G, M, a->xyz, a->scaling, a->rotation, a->times, a->P, a->T, a->deform_scale,
-                                                          means, scales, rots, nullptr, nullptr, nullptr);
+  deform_kernel<0><<<(n + 127) / 128, 128, smem, st>>>(G, M, globals(a, nullptr), a->xyz, a->scaling, a->rotation, a->times, a->P, a->T,
+                                                      a->deform_scale, means, scales, rots, nullptr, nullptr, nullptr);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_deform_featmean(const a3d_deform_args* a, float* featmean, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DeformGrids G; DeformMlp M;
+  if (int r = fill(a, &G, &M)) return r;
+  if (!featmean) return fail(A3D_EINVAL, "a3d_deform_featmean: null output");
+  if (a->P < 128) return fail(A3D_EINVAL, "a3d_deform_featmean: needs at least 128 gaussians (got %d)", a->P);
+  const int n = a->P * a->T;
+  A3D_CUDA_CHECK(cudaMemsetAsync(featmean, 0, sizeof(float) * a->T * a->num_scales * kFeat, st));
+  const size_t smem = (3 * kHid * kHid + 3 * 4 * kHid) * sizeof(float);
+  deform_kernel<2><<<(n + 127) / 128, 128, smem, st>>>(G, M, globals(a, featmean), a->xyz, a->scaling, a->rotation, a->times, a->P, a->T,
+                                                      a->deform_scale, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
@@ -279,11 +342,11 @@ extern "C" int a3d_deform_backward(const a3d_deform_args* a, const float* g_mean
   const size_t smem = 2 * (3 * kHid * kHid + 3 * 4 * kHid) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    A3D_CUDA_CHECK(cudaFuncSetAttribute(deform_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(deform_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  deform_kernel<true><<<(n + 127) / 128, 128, smem, st>>>(G, M, a->xyz, a->scaling, a->rotation, a->times, a->P, a->T, a->deform_scale,
-                                                         nullptr, nullptr, nullptr, g_means, g_scales, g_rots);
+  deform_kernel<1><<<(n + 127) / 128, 128, smem, st>>>(G, M, globals(a, nullptr), a->xyz, a->scaling, a->rotation, a->times, a->P, a->T,
+                                                      a->deform_scale, nullptr, nullptr, nullptr, g_means, g_scales, g_rots);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }

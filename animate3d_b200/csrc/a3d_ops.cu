@@ -313,27 +313,32 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int D>
-__global__ void __launch_bounds__(256) temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int heads,
-                                                             float scale_log2) {
+// HB heads per block (grid.y = heads / HB): 8 x 40, 4 x 80, 2 x 160 channels -> every block stages 16 x 960 halves (31 KB), so
+// the wide levels keep ~7 blocks per SM instead of one 123 KB block.
+template <int D, int HB>
+__global__ void __launch_bounds__(HB * 32) temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int heads,
+                                                                 float scale_log2) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int C = heads * D;
-  const int ld = 3 * C + 8;                    // padded row (halves)
+  constexpr int CB = HB * D;                   // channels of this block's heads
+  constexpr int ld = 3 * CB + 8;               // padded row (halves): [q | k | v] of the block's heads
   __half* sm = reinterpret_cast<__half*>(smraw);
   const int64_t pix = blockIdx.x;
-  const __half* base = qkv + pix * 16 * 3 * C;
-  const int vec_row = 3 * C / 8;
-  for (int i = threadIdx.x; i < 16 * vec_row; i += blockDim.x) {
-    const int f = i / vec_row, v = i % vec_row;
-    *reinterpret_cast<uint4*>(sm + f * ld + v * 8) = __ldg(reinterpret_cast<const uint4*>(base) + i);
+  const int hb0 = blockIdx.y * HB;
+  const __half* base = qkv + pix * 16 * 3 * C + hb0 * D;
+  constexpr int vseg = CB / 8;                 // 16-byte vectors per (row, q|k|v) segment
+  for (int i = threadIdx.x; i < 16 * 3 * vseg; i += blockDim.x) {
+    const int f = i / (3 * vseg), rem = i % (3 * vseg), part = rem / vseg, v = rem % vseg;
+    *reinterpret_cast<uint4*>(sm + f * ld + part * CB + v * 8) =
+        __ldg(reinterpret_cast<const uint4*>(base + (int64_t)f * 3 * C + (int64_t)part * C) + v);
   }
   __syncthreads();
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  if (h < heads) {
+  {
     const __half* q = sm + h * D;
-    const __half* k = sm + C + h * D;
-    const __half* v = sm + 2 * C + h * D;
+    const __half* k = sm + CB + h * D;
+    const __half* v = sm + 2 * CB + h * D;
     // ---- S = Q K^T: two 8-key n-tiles, ceil(D / 16) k-steps (the last one half empty when D % 16 == 8)
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int KS = (D + 15) / 16;
@@ -397,11 +402,10 @@ __global__ void __launch_bounds__(256) temporal_attn16_kernel(const __half* __re
     }
   }
   __syncthreads();
-  const int ovec = C / 8;
-  __half* obase = out + pix * 16 * C;
-  for (int i = threadIdx.x; i < 16 * ovec; i += blockDim.x) {
-    const int f = i / ovec, vv = i % ovec;
-    reinterpret_cast<uint4*>(obase)[i] = *reinterpret_cast<const uint4*>(sm + f * ld + vv * 8);
+  __half* obase = out + pix * 16 * C + hb0 * D;
+  for (int i = threadIdx.x; i < 16 * vseg; i += blockDim.x) {
+    const int f = i / vseg, vv = i % vseg;
+    *reinterpret_cast<uint4*>(obase + (int64_t)f * C + vv * 8) = *reinterpret_cast<const uint4*>(sm + f * ld + vv * 8);
   }
 }
 
@@ -601,14 +605,10 @@ extern "C" int a3d_layer_norm(const void* x, const float* gamma, const float* be
 
 template <int D>
 static int launch_temporal(const void* qkv, void* out, int64_t pixels, int frames, int heads, float scale, cudaStream_t st) {
-  if (frames == 16 && heads <= 8) {
-    const size_t smem16 = (size_t)16 * (3 * heads * D + 8) * 2;
-    static size_t max_set16 = 0;
-    if (smem16 > 48 * 1024 && smem16 > max_set16) {
-      A3D_CUDA_CHECK(cudaFuncSetAttribute(temporal_attn16_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-      max_set16 = smem16;
-    }
-    temporal_attn16_kernel<D><<<(unsigned)pixels, heads * 32, smem16, st>>>(
+  constexpr int HB = 320 / D;   // 8 / 4 / 2 heads per block
+  if (frames == 16 && heads % HB == 0 && heads / HB <= 65535) {
+    const size_t smem16 = (size_t)16 * (3 * HB * D + 8) * 2;   // 31 KB
+    temporal_attn16_kernel<D, HB><<<dim3((unsigned)pixels, (unsigned)(heads / HB)), HB * 32, smem16, st>>>(
         reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), heads, scale * 1.4426950408889634f);
     A3D_LAUNCH_CHECK();
     return A3D_OK;

@@ -211,9 +211,16 @@ typedef struct a3d_deform_args {
   float* grad_planes[12];  /* backward only; entries may be NULL */
   float* grad_w1[3];
   float* grad_w2[3];
+  /* `use_global_trans` support (gaussian_4d.py:499-511, 525-539); all optional (NULL = off) */
+  const float* rot_base;      /* [T,P,4] per-frame base quaternions, replace `rotation` (forward and backward) */
+  float* grad_rot_base;       /* backward: receives dL/d rot_base, [T,P,4] */
+  const float* grad_featmean; /* backward: dL/d (per-frame mean feature), [T, num_scales*channels]; folded into grad_planes */
 } a3d_deform_args;
 
 int a3d_deform_forward(const a3d_deform_args* args, float* means, float* scales, float* rotations, void* stream);
+/* per-frame mean over the P gaussians of the k-planes feature vector (`hidden_feats.mean(0)`, gaussian_4d.py:501, 527):
+ * featmean [T, num_scales*channels] */
+int a3d_deform_featmean(const a3d_deform_args* args, float* featmean, void* stream);
 int a3d_deform_backward(const a3d_deform_args* args, const float* dL_dmeans, const float* dL_dscales, const float* dL_drotations,
                         void* stream);
 

@@ -175,6 +175,18 @@ def load_kplanes_fns():
     return ns["interpolate_ms_features"]
 
 
+def load_rotation_fns():
+    """exec build_rotation / extract_rotation_torch / euler_angles_to_rotation_matrix out of geometry/utils.py (the module
+    imports scipy's Rotation at top level for an unrelated helper; only these three functions are needed)."""
+    src = open(os.path.join(REF, "custom/threestudio-animate3d/geometry/utils.py")).read()
+    tree = ast.parse(src)
+    want = {"build_rotation", "extract_rotation_torch", "euler_angles_to_rotation_matrix"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    ns = {"torch": torch, "math": math}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "geometry_utils_rot", "exec"), ns)
+    return ns["build_rotation"], ns["extract_rotation_torch"], ns["euler_angles_to_rotation_matrix"]
+
+
 def attn_weights(attn, prefix):
     return {f"{prefix}.to_q.weight": attn.to_q.weight.detach().clone(),
             f"{prefix}.to_k.weight": attn.to_k.weight.detach().clone(),
@@ -269,6 +281,22 @@ def main():
         feats = interp(None, pts, grids)
     torch.save({"grids": [[p.detach().clone() for p in pl] for pl in grids], "pts": pts, "feats": feats},
                os.path.join(OUT, "ref_kplanes.pt"))
+
+    # global rotation helpers of the use_global_trans branch (geometry/utils.py:33-62, 73-133, 135-167); the quaternions are
+    # chosen so that all four branches of the matrix -> quaternion conversion are exercised
+    build_rotation, extract_rotation, euler_to_matrix = load_rotation_fns()
+    g = torch.Generator().manual_seed(91)
+    quats = torch.randn(400, 4, generator=g)
+    quats[:40, 0] *= 0.01          # small real part -> negative trace branches
+    angles = torch.rand(6, 3, generator=g) * 2 * math.pi - math.pi
+    with torch.no_grad():
+        mats = build_rotation(quats)
+        rmats = torch.stack([euler_to_matrix(a) for a in angles])
+        rotated = torch.stack([extract_rotation(r @ mats) for r in rmats])
+        tr = (rmats[:, None] @ mats[None]).diagonal(dim1=-2, dim2=-1).sum(-1)
+    assert (tr <= 0).sum() > 20 and (tr > 0).sum() > 20
+    torch.save({"quats": quats, "angles": angles, "mats": mats, "rmats": rmats, "rotated": rotated},
+               os.path.join(OUT, "ref_rotation.pt"))
 
     get_camera = load_camera_fns()
     cam = {n: get_camera(n) for n in (1, 4, 8)}

@@ -6,12 +6,14 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-enum Op { MUFU, F2FP, FFMA, FFMA2, FMNMX3, LEA, MUFU_FFMA, MUFU_F2FP, MUFU2_F2FP_FFMA2, POLY, MIX50, MIX25, NOPS };
-static const char* kNames[] = {"MUFU.EX2", "F2FP.F16.F32.PACK", "FFMA", "FFMA2", "FMNMX3", "LEA/IADD", "MUFU+FFMA 1:1",
+enum Op { EX2H2, TANHH2, MUFU, F2FP, FFMA, FFMA2, FMNMX3, LEA, MUFU_FFMA, MUFU_F2FP, MUFU2_F2FP_FFMA2, POLY, MIX50, MIX25, NOPS };
+static const char* kNames[] = {"ex2.approx.ftz.f16x2", "tanh.approx.f16x2", "MUFU.EX2", "F2FP.F16.F32.PACK", "FFMA", "FFMA2", "FMNMX3", "LEA/IADD", "MUFU+FFMA 1:1",
                                "MUFU+F2FP 2:1", "softmax pair: FFMA2+2MUFU+F2FP+FMNMX3", "poly pair (13 ops)",
                                "mix: 1 mufu pair + 1 poly pair", "mix: 3 mufu pairs + 1 poly pair"};
 
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t ex2h2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t tanhh2(uint32_t x) { uint32_t y; asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 __device__ __forceinline__ uint32_t f2fp(float a, float b) { uint32_t r; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float ffma(float a, float b, float c) { float d; asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(1024, 1) bench(float* out, long long* cycles, 
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      if (OP == EX2H2) x[u] = __uint_as_float(ex2h2(__float_as_uint(x[u])));
+      if (OP == TANHH2) x[u] = __uint_as_float(tanhh2(__float_as_uint(x[u])));
       if (OP == MUFU) x[u] = ex2(x[u]);
       if (OP == F2FP) { acc ^= f2fp(x[u], x[(u + 1) % U]); x[u] = __uint_as_float(acc); }
       if (OP == FFMA) x[u] = ffma(x[u], seed, 0.5f);
@@ -113,6 +117,8 @@ int main() {
   cudaMalloc(&out, 148 * 1024 * 4);
   cudaMalloc(&cyc, 148 * 8);
   for (int w : {4, 8, 16}) {
+    run<EX2H2>(w, out, cyc, 1);
+    run<TANHH2>(w, out, cyc, 1);
     run<MUFU>(w, out, cyc, 1);
     run<F2FP>(w, out, cyc, 1);
     run<FFMA>(w, out, cyc, 1);
