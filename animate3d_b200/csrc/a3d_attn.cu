@@ -1574,7 +1574,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           // the same loop.  Only when a row's new max exceeds the stabiliser by more than kRescaleLog2 (P could overflow
           // fp16) is the step redone with the updated stabiliser -- after the first few steps that never happens.
           float mx0 = -INFINITY, mx1 = -INFINITY;
-          const float neg_m = -m_run;
+          const float neg_m = POLY == 3 ? -(m_run + kPackBias) : -m_run;
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
             uint4 q;
@@ -1586,7 +1586,15 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
               if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
               const bool poly = POLY == 1 ? (t == 1) : POLY == 2 ? (t & 1) : false;
               const float y0 = fmaf(s0, p.scale_log2, neg_m), y1 = fmaf(s1, p.scale_log2, neg_m);
-              qw[t] = poly ? pack_f16x2(exp2_fma(y0), exp2_fma(y1)) : pack_f16x2(ex2_approx(y0), ex2_approx(y1));
+              if (POLY == 3) {
+                // F2FP shares the MUFU pipe (4 of the 20 pipe cycles of a pair): pack on the ALU pipe instead.  neg_m carries
+                // an extra -112, so the fp32 bits of 2^(y-112) shifted right by 13 ARE the fp16 bits of 2^y (truncated; the
+                // bias of the truncation is common to the numerator and the row sum and cancels).
+                const uint32_t e0 = __float_as_uint(ex2_approx(y0)), e1 = __float_as_uint(ex2_approx(y1));
+                qw[t] = ((e1 << 3) & 0xFFFF0000u) | (e0 >> 13);
+              } else {
+                qw[t] = poly ? pack_f16x2(exp2_fma(y0), exp2_fma(y1)) : pack_f16x2(ex2_approx(y0), ex2_approx(y1));
+              }
             }
             *reinterpret_cast<uint4*>(sPg + sw128_offset(r, 4 * h + c16)) = q;
           }
@@ -2092,6 +2100,7 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
       if (attn_variant() == 3) return launch_attn3<40>(dev, a, mq, grid, st);
       if (attn_variant() == 4) return launch_attn4<40, 0>(dev, a, mq, grid, st);
       if (attn_mode() == 1) return launch_attn5<40, 1>(dev, a, mq, grid, st);
+      if (attn_mode() == 3) return launch_attn5<40, 3>(dev, a, mq, grid, st);
       return launch_attn5<40, 0>(dev, a, mq, grid, st);
     case 80:
       if (attn_variant() >= 4 && attn_variant80()) return launch_attn4<80, 0>(dev, a, mq, grid, st);
