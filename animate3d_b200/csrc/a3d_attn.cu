@@ -1841,6 +1841,168 @@ attn_fewkeys_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, int64_t os1, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Short-key attention (text cross-attention: 77 keys shared by the F frames of an image group).  A tcgen05 CTA would live for
+// two 64-key steps, so its set-up (TMEM allocation, barrier init, TMA round trips) dominated: 4096 CTAs x ~7 us.  Here the
+// 77 keys/values of a (key batch, head) are staged once per block in shared memory (zero-padded to 80 rows) and each warp
+// walks 16-row query tiles with mma.sync.m16n8k16: S (16 x 80) and P stay in registers, V^T fragments come from
+// ldmatrix.trans.  HBM-bound (Q in, O out).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kShortKeysPad = 80;
+template <int D>
+struct ShortCfg {
+  static constexpr int kLdw = (D / 2 + 31) / 32 * 32 + 4;      // row stride in 32-bit words: == 4 (mod 32) -> 8 rows x 4 words tile the banks
+  static constexpr int kLd = 2 * kLdw;                          // in halves
+  static constexpr int kSmem = 2 * kShortKeysPad * kLd * 2;     // K and V
+};
+
+template <int D>
+__global__ void __launch_bounds__(128)
+attn_shortkeys_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, int64_t os1, int64_t os2, int64_t os3, int64_t os4, int dqk,
+                      int dv, float scale_log2, int kv_div, int kv_i3_zero, int accumulate, float out_scale, int rows_per_block) {
+  using Cfg = ShortCfg<D>;
+  constexpr int LD = Cfg::kLd;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __half* sK = reinterpret_cast<__half*>(smraw);
+  __half* sV = sK + kShortKeysPad * LD;
+  const int Lq = q.e1 * q.e2, Lk = k.e1 * k.e2;
+  const int h = blockIdx.y, qb = blockIdx.z;
+  const int kb = qb / kv_div;
+  const int64_t koff = (int64_t)(kv_i3_zero ? 0 : kb % k.e3) * k.s3 + (int64_t)(kb / k.e3) * k.s4 + h * dqk;
+  const int64_t voff = (int64_t)(kv_i3_zero ? 0 : kb % v.e3) * v.s3 + (int64_t)(kb / v.e3) * v.s4 + h * dv;
+  constexpr int VPR = D / 8;   // 16-byte vectors per row
+  for (int i = threadIdx.x; i < kShortKeysPad * VPR; i += blockDim.x) {
+    const int j = i / VPR, c = i % VPR;
+    uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
+    if (j < Lk) {
+      kv4 = __ldg(reinterpret_cast<const uint4*>(k.base + koff + (int64_t)(j % k.e1) * k.s1 + (int64_t)(j / k.e1) * k.s2) + c);
+      vv4 = __ldg(reinterpret_cast<const uint4*>(v.base + voff + (int64_t)(j % v.e1) * v.s1 + (int64_t)(j / v.e1) * v.s2) + c);
+    }
+    *reinterpret_cast<uint4*>(sK + j * LD + c * 8) = kv4;
+    *reinterpret_cast<uint4*>(sV + j * LD + c * 8) = vv4;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(row_begin + rows_per_block, Lq);
+  const int64_t qbase = (int64_t)(qb % q.e3) * q.s3 + (int64_t)(qb / q.e3) * q.s4 + h * dqk;
+  const int64_t obase = (int64_t)(qb % q.e3) * os3 + (int64_t)(qb / q.e3) * os4 + h * D;
+  constexpr int KS = (D + 15) / 16;
+  constexpr int NT = kShortKeysPad / 8;    // 10 key n-tiles
+  for (int r0 = row_begin + warp * 16; r0 < row_end; r0 += 64) {
+    const int l_lo = r0 + g, l_hi = r0 + g + 8;
+    const bool ok_lo = l_lo < row_end, ok_hi = l_hi < row_end;
+    const __half* q_lo = q.base + qbase + (int64_t)(l_lo % q.e1) * q.s1 + (int64_t)(l_lo / q.e1) * q.s2;
+    const __half* q_hi = q.base + qbase + (int64_t)(l_hi % q.e1) * q.s1 + (int64_t)(l_hi / q.e1) * q.s2;
+    float s[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { s[nt][0] = 0.f; s[nt][1] = 0.f; s[nt][2] = 0.f; s[nt][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      const int d0 = kk * 16 + 2 * t;
+      const bool hi_half = (kk * 16 + 8) < D;       // second 8-column half of this k-step inside the head?
+      uint32_t a[4];
+      a[0] = ok_lo ? __ldg(reinterpret_cast<const uint32_t*>(q_lo + d0)) : 0u;
+      a[1] = ok_hi ? __ldg(reinterpret_cast<const uint32_t*>(q_hi + d0)) : 0u;
+      a[2] = (ok_lo && hi_half) ? __ldg(reinterpret_cast<const uint32_t*>(q_lo + d0 + 8)) : 0u;
+      a[3] = (ok_hi && hi_half) ? __ldg(reinterpret_cast<const uint32_t*>(q_hi + d0 + 8)) : 0u;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const __half* kr = sK + (nt * 8 + g) * LD + d0;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
+        const uint32_t b1 = hi_half ? *reinterpret_cast<const uint32_t*>(kr + 8) : 0u;
+        mma_16816(s[nt], a, b0, b1);
+      }
+    }
+    // ---- softmax over the Lk valid keys (columns nt*8 + 2t, +1); rows g (c0,c1) and g+8 (c2,c3) live in a quad
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int key = nt * 8 + 2 * t;
+      if (key >= Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (key + 1 >= Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, o));
+      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, o));
+    }
+    const float nl = -mx_lo * scale_log2, nh = -mx_hi * scale_log2;
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[nt][0] = ex2_approx(fmaf(s[nt][0], scale_log2, nl)); s[nt][1] = ex2_approx(fmaf(s[nt][1], scale_log2, nl));
+      s[nt][2] = ex2_approx(fmaf(s[nt][2], scale_log2, nh)); s[nt][3] = ex2_approx(fmaf(s[nt][3], scale_log2, nh));
+      sum_lo += s[nt][0] + s[nt][1];
+      sum_hi += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      sum_lo += __shfl_xor_sync(0xffffffffu, sum_lo, o);
+      sum_hi += __shfl_xor_sync(0xffffffffu, sum_hi, o);
+    }
+    const float inv_lo = 1.0f / sum_lo, inv_hi = 1.0f / sum_hi;
+    // P (normalised, fp16) as A fragments of the 5 key k-steps
+    uint32_t pa[NT / 2][4];
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      pa[kk][0] = pack_f16x2(s[2 * kk][0] * inv_lo, s[2 * kk][1] * inv_lo);
+      pa[kk][1] = pack_f16x2(s[2 * kk][2] * inv_hi, s[2 * kk][3] * inv_hi);
+      pa[kk][2] = pack_f16x2(s[2 * kk + 1][0] * inv_lo, s[2 * kk + 1][1] * inv_lo);
+      pa[kk][3] = pack_f16x2(s[2 * kk + 1][2] * inv_hi, s[2 * kk + 1][3] * inv_hi);
+    }
+    __half* o_lo = out + obase + (int64_t)(l_lo % q.e1) * os1 + (int64_t)(l_lo / q.e1) * os2;
+    __half* o_hi = out + obase + (int64_t)(l_hi % q.e1) * os1 + (int64_t)(l_hi / q.e1) * os2;
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < NT / 2; ++kk) {
+        const uint32_t addr = smem_u32(sV + (kk * 16 + (lane & 15)) * LD + nt * 8);
+        uint32_t b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+        mma_16816(o, pa[kk], b0, b1);
+      }
+      const int col = nt * 8 + 2 * t;
+      if (ok_lo) {
+        float x0 = o[0] * out_scale, x1 = o[1] * out_scale;
+        if (accumulate) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(o_lo + col)); x0 += f.x; x1 += f.y; }
+        *reinterpret_cast<uint32_t*>(o_lo + col) = pack_f16x2(x0, x1);
+      }
+      if (ok_hi) {
+        float x0 = o[2] * out_scale, x1 = o[3] * out_scale;
+        if (accumulate) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(o_hi + col)); x0 += f.x; x1 += f.y; }
+        *reinterpret_cast<uint32_t*>(o_hi + col) = pack_f16x2(x0, x1);
+      }
+    }
+  }
+}
+
+template <int D>
+static int launch_shortkeys(const a3d_attn_args* a, int dqk, int dv, int kv_div, int batches, cudaStream_t st) {
+  using Cfg = ShortCfg<D>;
+  ViewDev q{reinterpret_cast<const __half*>(a->q.base), a->q.s1, a->q.s2, a->q.s3, a->q.s4, a->q.e1, a->q.e2, a->q.e3, a->q.e4};
+  ViewDev k{reinterpret_cast<const __half*>(a->k.base), a->k.s1, a->k.s2, a->k.s3, a->k.s4, a->k.e1, a->k.e2, a->k.e3, a->k.e4};
+  ViewDev v{reinterpret_cast<const __half*>(a->v.base), a->v.s1, a->v.s2, a->v.s3, a->v.s4, a->v.e1, a->v.e2, a->v.e3, a->v.e4};
+  static bool attr_set = false;
+  if (!attr_set && Cfg::kSmem > 48 * 1024) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn_shortkeys_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_set = true;
+  }
+  const int Lq = a->q.e1 * a->q.e2;
+  int rows_per_block = 256;                       // 4 x 64-row rounds per block amortise the K/V staging
+  while (rows_per_block > 64 && (int64_t)((Lq + rows_per_block - 1) / rows_per_block) * a->heads * batches < 1184) rows_per_block /= 2;
+  dim3 grid((unsigned)((Lq + rows_per_block - 1) / rows_per_block), (unsigned)a->heads, (unsigned)batches);
+  attn_shortkeys_kernel<D><<<grid, 128, Cfg::kSmem, st>>>(q, k, v, reinterpret_cast<__half*>(a->out), a->os1, a->os2, a->os3, a->os4,
+                                                          dqk, dv, a->scale * 1.4426950408889634f, kv_div, a->kv_i3_zero,
+                                                          a->accumulate, a->out_scale == 0.f ? 1.f : a->out_scale, rows_per_block);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
 static int tile_geom(const a3d_view5& v, int* box1, int* box2, int* t1, int* tiles, int* rows) {
   if (v.e1 >= 128) {
     if (v.e1 % 128) return fail(A3D_EINVAL, "a3d_attention: inner extent %d must be a multiple of 128", v.e1);
@@ -2052,7 +2214,10 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
 
   if ((a->os1 | a->os2 | a->os3 | a->os4) % 8 || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
-  if (a->k.e1 * a->k.e2 <= kFewKeysMax) {
+  // impl == AUTO picks the kernel by key count; an explicit A3D_GEMM_TCGEN05 forces the tcgen05 kernels (tests use it to keep
+  // their ragged-key paths covered)
+  const bool auto_impl = a->impl == A3D_GEMM_AUTO;
+  if (auto_impl && a->k.e1 * a->k.e2 <= kFewKeysMax) {
     // a handful of keys (IP-adapter image tokens): HBM-bound thread-per-(row, head) kernel, see attn_fewkeys_kernel
     if ((a->q.s1 | a->q.s2 | a->q.s3 | a->q.s4 | a->k.s1 | a->k.s2 | a->k.s3 | a->k.s4 | a->v.s1 | a->v.s2 | a->v.s3 | a->v.s4) % 8 ||
         ((reinterpret_cast<uintptr_t>(a->q.base) | reinterpret_cast<uintptr_t>(a->k.base) | reinterpret_cast<uintptr_t>(a->v.base)) & 15))
@@ -2066,6 +2231,18 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
         a->scale * 1.4426950408889634f, kv_div, a->kv_i3_zero, a->accumulate, a->out_scale == 0.f ? 1.f : a->out_scale);
     A3D_LAUNCH_CHECK();
     return A3D_OK;
+  }
+  if (auto_impl && a->k.e1 * a->k.e2 <= kShortKeysPad && (a->os1 | a->os2) % 2 == 0 &&
+      ((a->k.s1 | a->k.s2 | a->k.s3 | a->k.s4 | a->v.s1 | a->v.s2 | a->v.s3 | a->v.s4) % 8 == 0) &&
+      ((a->q.s1 | a->q.s2 | a->q.s3 | a->q.s4) % 2 == 0) &&
+      ((reinterpret_cast<uintptr_t>(a->k.base) | reinterpret_cast<uintptr_t>(a->v.base)) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(a->q.base) & 3) == 0 && batches <= 65535) {
+    // 9..80 keys (text cross-attention): warp-level MMA kernel with the keys resident in shared memory
+    switch (d) {
+      case 40: return launch_shortkeys<40>(a, dqk, dv, kv_div, batches, st);
+      case 80: return launch_shortkeys<80>(a, dqk, dv, kv_div, batches, st);
+      default: return launch_shortkeys<160>(a, dqk, dv, kv_div, batches, st);
+    }
   }
 
   AttnDev dev;

@@ -249,6 +249,14 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, bo
          | ((M >> 4) << 24);                // m_dim
 }
 
+// legacy warp-level MMA (fp16 x fp16 -> fp32), used where a problem is far below a tcgen05 tile (16-frame temporal
+// attention, 77-key text cross-attention)
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // byte offset of logical element (row r, 16-byte chunk c16 in [0,8)) inside a SWIZZLE_128B K-major tile whose base is
 // 1024-byte aligned: Swizzle<3,4,3> XORs address bits [4,7) with bits [7,10).
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c16) { return r * 128u + ((c16 ^ (r & 7u)) << 4); }

@@ -307,11 +307,6 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
 // fragment loads of the 8 row groups hit different banks); S and P never leave registers (the accumulator fragment of QK^T
 // is exactly the A fragment of P V); the normalised O goes back over the head's dead Q slice and leaves with coalesced
 // 16-byte stores.  ~100 warp instructions per (pixel, head) instead of ~1500 in the scalar kernel: HBM-bound.
-__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 // HB heads per block (grid.y = heads / HB): 8 x 40, 4 x 80, 2 x 160 channels -> every block stages 16 x 960 halves (31 KB), so
 // the wide levels keep ~7 blocks per SM instead of one 123 KB block.

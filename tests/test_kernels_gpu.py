@@ -240,7 +240,7 @@ def test_cross_view_attention(case, impl, layout):
     close(out, ref2, what=f"i2v attention {name} {impl} {layout}")
 
 
-@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "auto", "simt"])
 @pytest.mark.parametrize("case", [(2, 3, 1024, 40, 77), (2, 2, 256, 80, 77), (3, 2, 64, 160, 4), (2, 2, 16, 160, 77),
                                   (2, 3, 1024, 40, 4), (3, 2, 256, 80, 4), (2, 2, 64, 160, 8), (2, 2, 256, 40, 16)],
                          ids=lambda c: "bn%d_f%d_hw%d_d%d_k%d" % c)
@@ -261,8 +261,8 @@ def test_cross_attention_text_keys(case, impl):
     vv = ops.view5(kvbuf, 2 * heads * dqk, ldk - 2 * heads * dqk, (ldk, Lk * ldk, Lk * ldk, Lk * ldk), (Lk, 1, 1, BN))
     out = torch.zeros(rows, C, device=DEV, dtype=torch.float16)
     scale = d ** -0.5
-    ops.attention(vq, vk, vv, out, (C, hw * C, hw * C, Fr * hw * C), heads=heads, d=d, scale=scale, kv_div=Fr,
-                  impl=L.IMPL_TC if impl == "tc" else L.IMPL_SIMT)
+    im = {"tc": L.IMPL_TC, "auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT}[impl]   # auto = few-keys / short-keys kernels
+    ops.attention(vq, vk, vv, out, (C, hw * C, hw * C, Fr * hw * C), heads=heads, d=d, scale=scale, kv_div=Fr, impl=im)
     qq = q[:, 0].reshape(BN, Fr, hw, heads, d).permute(0, 1, 3, 2, 4)                  # [BN, F, H, hw, d]
     kk = k.reshape(BN, 1, Lk, heads, d).permute(0, 1, 3, 2, 4).expand(BN, Fr, heads, Lk, d)
     vv_ = v.reshape(BN, 1, Lk, heads, d).permute(0, 1, 3, 2, 4).expand(BN, Fr, heads, Lk, d)
@@ -273,7 +273,7 @@ def test_cross_attention_text_keys(case, impl):
     close(out, ref, what=f"cross attention {case} {impl}")
     # IP-adapter use: a second key set accumulated onto the first result with a scale (attention_processor.py:218-238)
     ops.attention(vq, vk, vv, out, (C, hw * C, hw * C, Fr * hw * C), heads=heads, d=d, scale=scale, kv_div=Fr,
-                  accumulate=True, out_scale=0.25, impl=L.IMPL_TC if impl == "tc" else L.IMPL_SIMT)
+                  accumulate=True, out_scale=0.25, impl=im)
     torch.cuda.synchronize()
     close(out, 1.25 * ref, what=f"accumulated cross attention {case} {impl}")
 
