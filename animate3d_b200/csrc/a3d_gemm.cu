@@ -38,6 +38,10 @@ struct GemmDev {
   void* C; int64_t ldc;
   int geglu, out_f32;
   int64_t perm_a, perm_b;
+  long long* trace;   // debug: per-tile clock64 timestamps of CTA 0 (null in production), see a3d_debug_set_gemm_trace
+  int dbg_nostore;    // debug (A3D_GEMM_NOSTORE=1): compute the epilogue but skip the global stores -- timing experiments only
+  int tma_store;      // epilogue writes through shared memory + TMA bulk stores (full 128-byte lines, asynchronous)
+  int stages;         // depth of the TMA -> MMA operand ring
 };
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below fp16 output
@@ -65,7 +69,11 @@ constexpr int kBK = 64;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 160 ? 5 : 6);
+  // Ring depth is a launch parameter (GemmDev::stages): short-K GEMMs do not react to it at all (measured 2/3/4 stages at
+  // BN = 256, profiles/r01_gemm_epilogue.txt) and give one stage to the TMA-store staging; the long-K implicit convolutions
+  // (5-D TMA boxes, longer latency) keep the deep ring and store directly.
+  static constexpr int kMaxStages = (BN == 256) ? 4 : (BN == 160 ? 5 : 6);
+  static constexpr int kStagesStaged = (BN == 256) ? 3 : (BN == 160 ? 5 : 5);
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -73,7 +81,11 @@ struct GemmCfg {
   static constexpr int kStageOut = 2048;   // 2 x 256 fp32 bias values (double-buffered with the accumulator)
   static constexpr int kRbLd = BN + 8;      // padded row of the staged row-bias slice (staggers the banks of the <=16 slots)
   static constexpr int kRbBytes = 16 * kRbLd * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + kRbBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // output staging for the TMA-store epilogue: one 32-row x 64-column (128 B per row, 128B-swizzled) box per epilogue warp
+  static constexpr int kOutStage = (BN == 160) ? 0 : 8 * 4096;
+  static constexpr int kTail = kStageOut + kRbBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int smem_bytes(bool staged) { return (staged ? kStagesStaged * kStageBytes + kOutStage : kMaxStages * kStageBytes) + kTail; }
+  static constexpr int kSmemBytes = smem_bytes(true) > smem_bytes(false) ? smem_bytes(true) : smem_bytes(false);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -83,18 +95,21 @@ enum { kEpiPlain = 0, kEpiRes = 1, kEpiGeglu = 2, kEpiF32 = 3 };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(320, 1)
-gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapC) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;
+  const int kStages = p.stages;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint8_t* smem_out = smem + kStages * Cfg::kStageBytes;           // [8 warps][32 rows][128 B], 1024-byte aligned
+  uint8_t* smem_stage = smem_out + (p.tma_store ? Cfg::kOutStage : 0);
   float* smem_rb = reinterpret_cast<float*>(smem_stage + Cfg::kStageOut);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStageOut + Cfg::kRbBytes);
   uint64_t* full_bar = bars;                       // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* empty_bar = bars + kStages;            // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;        // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -105,7 +120,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -145,7 +160,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
             tma_load_5d(smem_a + stage * Cfg::kABytes, &mapA, &full_bar[stage], kb * kBK, mt * kBM, 0, 0, 0);
           }
           tma_load_5d(smem_b + stage * Cfg::kBBytes, &mapB, &full_bar[stage], kb * kBK, nt * BN, 0, 0, 0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -157,8 +172,12 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const bool tr = p.trace && blockIdx.x == 0 && tcount < 60;
+        if (tr) p.trace[tcount * 16 + 8] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (tr) p.trace[tcount * 16 + 9] = clock64();
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -172,9 +191,11 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
             umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
+          if (kb == 0 && tr) p.trace[tcount * 16 + 10] = clock64();
           if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[acc]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        if (tr) p.trace[tcount * 16 + 11] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -188,9 +209,13 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
     const int half = warp >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
+      const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && tcount < 60;
+      if (tr) p.trace[tcount * 16 + 0] = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (tr) p.trace[tcount * 16 + 1] = clock64();
       tc_fence_after();
       const int64_t row0 = (int64_t)mt * kBM + quad * 32;
       const int64_t row = row0 + lane;
@@ -227,36 +252,37 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         if (threadIdx.x < BN) sb[threadIdx.x] = bc < p.N ? __ldg(p.bias + bc) : 0.f;
       }
       if (p.bias || p.rb_stage) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tr) p.trace[tcount * 16 + 2] = clock64();
 
-      // fp32 values of 32 accumulator columns -> + bias + rowbias, * scale
-      auto finish32 = [&](uint32_t* r, int64_t col0) {
-        float* v = reinterpret_cast<float*>(r);
-        if (col0 + 32 <= p.N) {
+      // fp32 values of NC (16 or 32) consecutive accumulator columns -> + bias + rowbias, * scale
+      auto finish = [&](float* v, int64_t col0, auto nc_tag) {
+        constexpr int NC = decltype(nc_tag)::value;
+        if (col0 + NC <= p.N) {
           if (p.bias) {
             const float4* bs = reinterpret_cast<const float4*>(sb + (col0 - (int64_t)nt * BN));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = bs[i];
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            for (int i = 0; i < NC / 4; ++i) {
+              const float4 bv = bs[i];
+              v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
             }
           }
           if (rbs) {
             const float4* rb = reinterpret_cast<const float4*>(rbs + (col0 - (int64_t)nt * BN));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = rb[i];
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            for (int i = 0; i < NC / 4; ++i) {
+              const float4 bv = rb[i];
+              v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
             }
           } else if (p.rowbias) {
             const float4* rb = reinterpret_cast<const float4*>(p.rowbias + rbrow * p.rb_ld + col0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(rb + i);
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            for (int i = 0; i < NC / 4; ++i) {
+              const float4 bv = __ldg(rb + i);
+              v[4 * i] += bv.x; v[4 * i + 1] += bv.y; v[4 * i + 2] += bv.z; v[4 * i + 3] += bv.w;
             }
           }
         } else {
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < NC; ++i) {
             if (col0 + i < p.N) {
               if (p.bias) v[i] += __ldg(p.bias + col0 + i);
               if (p.rowbias) v[i] += __ldg(p.rowbias + rbrow * p.rb_ld + col0 + i);
@@ -265,49 +291,62 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         }
         if (p.acc_scale != 1.0f) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
+          for (int i = 0; i < NC; ++i) v[i] *= p.acc_scale;
         }
       };
+      using N16 = std::integral_constant<int, 16>;
+      using N32 = std::integral_constant<int, 32>;
       const int64_t orow = (EPI == kEpiRes && row_ok) ? perm_row(row, p.perm_a, p.perm_b) : row;
-      // 32 finished fp32 values of this thread's row -> (+ residuals) -> fp16 -> two 256-bit stores (two full sectors)
-      auto store32 = [&](uint32_t* r, const uint32_t* r1, const uint32_t* r2, int64_t ocol) {
-        float* v = reinterpret_cast<float*>(r);
+      // NC finished fp32 values of this thread's row -> (+ residuals) -> fp16 -> 256-bit stores (whole 32-byte sectors)
+      auto store = [&](float* v, const uint32_t* r1, const uint32_t* r2, int64_t ocol, auto nc_tag) {
+        constexpr int NC = decltype(nc_tag)::value;
         if (EPI == kEpiRes && p.R1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < NC / 2; ++i) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r1[i]));
             v[2 * i] += p.r1_scale * f.x; v[2 * i + 1] += p.r1_scale * f.y;
           }
         }
         if (EPI == kEpiRes && p.R2) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < NC / 2; ++i) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r2[i]));
             v[2 * i] += f.x; v[2 * i + 1] += f.y;
           }
         }
-        uint32_t h[16];
+        uint32_t h[NC / 2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+        for (int i = 0; i < NC / 2; ++i) h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+        if (p.dbg_nostore && h[0] != 0x12345678u) return;
+        if (Cfg::kOutStage && p.tma_store) {
+          // this row's NC halves into the warp's staging box: 16-byte chunks (ocol % 64) / 8 .. of row `lane`
+          uint8_t* box = smem_out + (warp & 7) * 4096;
+          const int c16 = (int)(ocol & 63) >> 3;      // tiles start on multiples of 64 columns (BN = 128 / 256)
+#pragma unroll
+          for (int i = 0; i < NC / 8; ++i)
+            *reinterpret_cast<uint4*>(box + sw128_offset(lane, c16 + i)) = *reinterpret_cast<const uint4*>(h + 4 * i);
+          return;
+        }
         __half* o = reinterpret_cast<__half*>(p.C) + orow * p.ldc + ocol;
-        if (ocol + 32 <= n_out) {
-          st_global_256(o, h);
-          st_global_256(o + 16, h + 8);
+        if (ocol + NC <= n_out) {
+#pragma unroll
+          for (int i = 0; i < NC / 16; ++i) st_global_256(o + 16 * i, h + 8 * i);
         } else {
-          for (int i = 0; i < 32; ++i) if (ocol + i < n_out) o[i] = reinterpret_cast<const __half*>(h)[i];
+          for (int i = 0; i < NC; ++i) if (ocol + i < n_out) o[i] = reinterpret_cast<const __half*>(h)[i];
         }
       };
+      // residual tiles: 16 columns (one 256-bit load each) per unit
       auto load_res = [&](uint32_t* r1, uint32_t* r2, int64_t ocol) {
-        if (ocol + 32 > n_out) {   // ragged tail: scalar fill
-          for (int i = 0; i < 32; ++i) {
+        if (ocol + 16 > n_out) {   // ragged tail: scalar fill
+          for (int i = 0; i < 16; ++i) {
             const bool ok = ocol + i < n_out;
             if (p.R1) reinterpret_cast<__half*>(r1)[i] = ok ? p.R1[row * p.ldr1 + ocol + i] : __float2half(0.f);
             if (p.R2) reinterpret_cast<__half*>(r2)[i] = ok ? p.R2[orow * p.ldr2 + ocol + i] : __float2half(0.f);
           }
           return;
         }
-        if (p.R1) { ld_global_256(p.R1 + row * p.ldr1 + ocol, r1); ld_global_256(p.R1 + row * p.ldr1 + ocol + 16, r1 + 8); }
-        if (p.R2) { ld_global_256(p.R2 + orow * p.ldr2 + ocol, r2); ld_global_256(p.R2 + orow * p.ldr2 + ocol + 16, r2 + 8); }
+        if (p.R1) ld_global_256(p.R1 + row * p.ldr1 + ocol, r1);
+        if (p.R2) ld_global_256(p.R2 + orow * p.ldr2 + ocol, r2);
       };
 
       if constexpr (EPI == kEpiF32) {
@@ -321,54 +360,105 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           tmem_wait_ld();
           const int64_t col0 = (int64_t)nt * BN + ch * 32;
           if (row_ok && col0 < p.N) {
-            finish32(r, col0);
+            finish(reinterpret_cast<float*>(r), col0, N32{});
             float* o = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
             for (int i = 0; i < 32; ++i) if (col0 + i < p.N) o[i] = __uint_as_float(r[i]);
           }
         }
-      } else if constexpr (EPI != kEpiGeglu) {
-        constexpr int U = BN / 32;                                  // 32-column units: 8 / 5 / 4
-        const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
-#pragma unroll 1
-        for (int u = u0; u < u1; ++u) {
-          const int64_t col0 = (int64_t)nt * BN + u * 32;
-          if (col0 >= p.N) break;
-          uint32_t r[32], r1[16], r2[16];
-          tmem_ld32(taddr + u * 32, r);
-          if constexpr (EPI == kEpiRes) { if (row_ok) load_res(r1, r2, col0); }
-          tmem_wait_ld();
-          if (row_ok) {
-            finish32(r, col0);
-            store32(r, r1, r2, col0);
-          }
-        }
       } else {
-        // GEGLU: accumulator columns come as (u[32] | g[32]) blocks -> 32 outputs per block
-        constexpr int UG = BN / 64;                                 // 4 or 2 blocks per tile
-        const int b0 = half ? UG / 2 : 0, b1 = half ? UG : UG / 2;
-#pragma unroll 1
-        for (int b = b0; b < b1; ++b) {
-          const int64_t col0 = (int64_t)nt * BN + b * 64;
-          if (col0 >= p.N) break;
-          uint32_t ru[32], rg[32], r1[16], r2[16];
-          tmem_ld32(taddr + b * 64, ru);
-          tmem_ld32(taddr + b * 64 + 32, rg);
-          tmem_wait_ld();
-          if (row_ok) {
-            finish32(ru, col0);
-            finish32(rg, col0 + 32);
+        // Units of accumulator columns, split between the two warps of a quadrant.  Plain: 32 output columns per unit;
+        // residual epilogue: 16 (keeps accumulators + two residual tiles double-buffered inside the register budget);
+        // GEGLU: accumulator columns come as (u[32] | g[32]) blocks and a unit is half a block (16 u + 16 g columns -> 16
+        // outputs).  The TMEM load (and the residual loads) of unit u+1 are issued BEFORE unit u is finished and stored:
+        // with two epilogue warps per sub-partition nothing else hides the TMEM / L2 latency, and the K = 320 GEMMs of
+        // level 0 were bound by exactly this chain.
+        constexpr bool kG = EPI == kEpiGeglu;
+        constexpr bool kR = EPI == kEpiRes;
+        constexpr int W = kR ? 16 : 32;          // accumulator columns per unit (GEGLU: 16 + 16)
+        constexpr int U = BN / W;
+        const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
+        auto acc_col = [&](int u) -> int64_t {   // first accumulator column of the unit's (first) column group
+          return (int64_t)nt * BN + (kG ? (u >> 1) * 64 + 16 * (u & 1) : u * W);
+        };
+        auto issue = [&](uint32_t* r, uint32_t* r1, uint32_t* r2, int u) {
+          if (kG) {
+            tmem_ld16p(taddr + (u >> 1) * 64 + 16 * (u & 1), r);
+            tmem_ld16p(taddr + (u >> 1) * 64 + 32 + 16 * (u & 1), r + 16);
+          } else if (kR) {
+            tmem_ld16p(taddr + u * 16, r);
+            if (row_ok && acc_col(u) < p.N) load_res(r1, r2, acc_col(u));
+          } else {
+            tmem_ld32p(taddr + u * 32, r);
+          }
+        };
+        auto process = [&](uint32_t* r, uint32_t* r1, uint32_t* r2, int u) {
+          const int64_t col0 = acc_col(u);
+          if (!row_ok || col0 >= p.N) return;
+          float* v = reinterpret_cast<float*>(r);
+          if (kG) {
+            finish(v, col0, N16{});
+            finish(v + 16, col0 + 32, N16{});
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ru[i] = __float_as_uint(__uint_as_float(ru[i]) * gelu_erf(__uint_as_float(rg[i])));
-            store32(ru, r1, r2, col0 / 2);
+            for (int i = 0; i < 16; ++i) v[i] *= gelu_erf(v[16 + i]);
+            store(v, r1, r2, ((int64_t)nt * BN + (u >> 1) * 64) / 2 + 16 * (u & 1), N16{});
+          } else if (kR) {
+            finish(v, col0, N16{});
+            store(v, r1, r2, col0, N16{});
+          } else {
+            finish(v, col0, N32{});
+            store(v, r1, r2, col0, N32{});
+          }
+        };
+        // TMA-store epilogue: a 64-column group of the warp's 32 rows (one 128-byte line per row) is complete after the
+        // unit whose columns end on a multiple of 64; lane 0 then hands the box to the TMA engine and the warp moves on.
+        // Stores leave the SM as whole lines, asynchronously (the direct 256-bit stores -- 32 different lines per
+        // instruction -- cost the K = 320 GEMMs a third of their time, profiles/r01_gemm_epilogue.txt).
+        const bool staged = Cfg::kOutStage && p.tma_store;
+        auto group_done = [&](int u) {
+          if (!staged) return;
+          const int64_t cend = acc_col(u) + W;                       // one past the unit's last accumulator column
+          if ((cend - (int64_t)nt * BN) % 64 != 0) return;
+          const int64_t gcol = cend - 64;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && gcol < n_out) {
+            tma_store_5d(&mapC, smem_out + (warp & 7) * 4096, (int)gcol, (int)row0, 0, 0, 0);
+            tma_store_commit();
+          }
+        };
+        // before the first write of a group: the TMA engine must have finished READING the warp's box (previous group)
+        auto group_begin = [&](int u) {
+          if (!staged || (acc_col(u) - (int64_t)nt * BN) % 64 != 0) return;
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        };
+        uint32_t ra[kR ? 16 : 32], rb[kR ? 16 : 32];
+        uint32_t r1a[kR ? 8 : 1], r2a[kR ? 8 : 1], r1b[kR ? 8 : 1], r2b[kR ? 8 : 1];
+        if (u0 < u1) issue(ra, r1a, r2a, u0);
+#pragma unroll 1
+        for (int u = u0; u < u1; u += 2) {
+          tmem_wait_ld();
+          if (u + 1 < u1) issue(rb, r1b, r2b, u + 1);
+          group_begin(u);
+          process(ra, r1a, r2a, u);
+          group_done(u);
+          if (u + 1 < u1) {
+            tmem_wait_ld();
+            if (u + 2 < u1) issue(ra, r1a, r2a, u + 2);
+            group_begin(u + 1);
+            process(rb, r1b, r2b, u + 1);
+            group_done(u + 1);
           }
         }
       }
+      if (tr) p.trace[tcount * 16 + 3] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+  if (Cfg::kOutStage && p.tma_store && warp < 8 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -425,7 +515,8 @@ __global__ void gemm_simt_kernel(const GemmDev p, const __half* __restrict__ A, 
 }
 
 template <int BN, int EPI>
-static int launch_tc_epi(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, cudaStream_t st) {
+static int launch_tc_epi(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, const CUtensorMap* mapC,
+                         cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -434,20 +525,31 @@ static int launch_tc_epi(const GemmDev& dev, const CUtensorMap* mapA, const CUte
   }
   const int tiles = dev.tiles_m * dev.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, EPI><<<grid, 320, Cfg::kSmemBytes, st>>>(dev, *mapA, *mapB);
+  GemmDev d2 = dev;
+  d2.stages = dev.tma_store ? Cfg::kStagesStaged : Cfg::kMaxStages;
+  gemm_tc_kernel<BN, EPI><<<grid, 320, Cfg::smem_bytes(dev.tma_store != 0), st>>>(d2, *mapA, *mapB, *mapC);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
 
 template <int BN>
-static int launch_tc(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, cudaStream_t st) {
-  if (dev.out_f32) return launch_tc_epi<BN, kEpiF32>(dev, mapA, mapB, st);
-  if (dev.geglu) return launch_tc_epi<BN, kEpiGeglu>(dev, mapA, mapB, st);
-  if (dev.R1 || dev.R2 || dev.perm_a) return launch_tc_epi<BN, kEpiRes>(dev, mapA, mapB, st);
-  return launch_tc_epi<BN, kEpiPlain>(dev, mapA, mapB, st);
+static int launch_tc(const GemmDev& dev, const CUtensorMap* mapA, const CUtensorMap* mapB, const CUtensorMap* mapC,
+                     cudaStream_t st) {
+  if (dev.out_f32) return launch_tc_epi<BN, kEpiF32>(dev, mapA, mapB, mapC, st);
+  if (dev.geglu) return launch_tc_epi<BN, kEpiGeglu>(dev, mapA, mapB, mapC, st);
+  if (dev.R1 || dev.R2 || dev.perm_a) return launch_tc_epi<BN, kEpiRes>(dev, mapA, mapB, mapC, st);
+  return launch_tc_epi<BN, kEpiPlain>(dev, mapA, mapB, mapC, st);
 }
 
+static long long* g_gemm_trace = nullptr;
+
 }  // namespace a3d
+
+// debug hook (not part of the product path): per-tile clock64 timestamps of CTA 0 of the following tcgen05 GEMM launches
+extern "C" int a3d_debug_set_gemm_trace(void* device_buffer_1024_int64) {
+  a3d::g_gemm_trace = reinterpret_cast<long long*>(device_buffer_1024_int64);
+  return A3D_OK;
+}
 
 extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   using namespace a3d;
@@ -466,6 +568,12 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   d.R2 = reinterpret_cast<const __half*>(a->R2); d.ldr2 = a->ldr2;
   d.C = a->C; d.ldc = a->ldc; d.geglu = a->geglu; d.out_f32 = a->out_f32;
   d.perm_a = a->perm_a; d.perm_b = a->perm_b;
+  d.trace = g_gemm_trace;
+  {
+    static int nostore = -1;
+    if (nostore < 0) { const char* e = getenv("A3D_GEMM_NOSTORE"); nostore = e ? atoi(e) : 0; }
+    d.dbg_nostore = nostore;
+  }
   if (a->geglu && (a->out_f32 || a->R1 || a->R2 || a->perm_a || (a->N % 128)))
     return fail(A3D_EINVAL, "a3d_gemm: GEGLU epilogue takes bias / row-bias only, fp16 output, N %% 128 == 0");
   if (a->out_f32 && (a->R1 || a->R2 || a->perm_a))
@@ -573,9 +681,26 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
     ka.estr[1] = cv.s; ka.estr[2] = cv.s;
     if (int r = get_tensor_map(ka, &mapA)) return r;
   }
+  // output through shared memory + TMA bulk stores where the epilogue allows it (plain / residual, no row permutation)
+  const CUtensorMap* mapC = mapA;
+  d.tma_store = 0;
+  {
+    static int want = -1;
+    if (want < 0) { const char* e = getenv("A3D_GEMM_TMA_STORE"); want = e ? atoi(e) : 1; }
+    // short-K GEMMs are bound by their output stores; the long-K ones (convolutions) keep the deeper operand ring instead
+    if (want && BN != 160 && a->K <= 1280 && !a->geglu && !a->out_f32 && !a->perm_a && (a->ldc % 8 == 0) &&
+        ((reinterpret_cast<uintptr_t>(a->C) & 15) == 0) && (a->N % 8 == 0)) {
+      const uint64_t dims[5] = {(uint64_t)a->N, (uint64_t)a->M, 1, 1, 1};
+      const uint64_t str[4] = {(uint64_t)a->ldc, (uint64_t)a->ldc * a->M, (uint64_t)a->ldc * a->M, (uint64_t)a->ldc * a->M};
+      const uint32_t box[5] = {64, 32, 1, 1, 1};
+      MapKey kc = make_key(a->C, dims, str, box);
+      if (int r = get_tensor_map(kc, &mapC)) return r;
+      d.tma_store = 1;
+    }
+  }
   switch (BN) {
-    case 256: return launch_tc<256>(d, mapA, mapB, st);
-    case 160: return launch_tc<160>(d, mapA, mapB, st);
-    default: return launch_tc<128>(d, mapA, mapB, st);
+    case 256: return launch_tc<256>(d, mapA, mapB, mapC, st);
+    case 160: return launch_tc<160>(d, mapA, mapB, mapC, st);
+    default: return launch_tc<128>(d, mapA, mapB, mapC, st);
   }
 }

@@ -464,66 +464,114 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restr
   if (idx < n) y[idx] = __float2half_rn(x[idx]);
 }
 
-// conv_in: sample [BN, Cin, F, H, W] fp32 -> y NHWC fp16 [(BN F) H W, Cout]
-__global__ void conv_in_kernel(const float* __restrict__ sample, const float* __restrict__ w, const float* __restrict__ b,
-                               __half* __restrict__ y, int bn, int cin, int f, int h, int wd, int cout) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)bn * f * h * wd * cout;
-  if (idx >= total) return;
-  const int co = (int)(idx % cout);
-  const int64_t pix = idx / cout;
+// conv_in: sample [BN, Cin, F, H, W] fp32 -> y NHWC fp16 [(BN F) H W, Cout].  Lanes = consecutive pixels (coalesced input
+// reads), a thread produces 16 output channels (one full 32-byte sector): its Cin*9 inputs sit in registers, the weights of
+// the block's channel slice in shared memory as [cin*9][16] (all lanes read the same address -> broadcast).
+constexpr int kConvInMaxK = 72;   // cin * 9 <= 72 (cin <= 8)
+__global__ void __launch_bounds__(128)
+conv_in_kernel(const float* __restrict__ sample, const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ y,
+               int bn, int cin, int f, int h, int wd, int cout) {
+  __shared__ __align__(16) float sw[kConvInMaxK * 16];
+  __shared__ float sb[16];
+  const int co0 = blockIdx.y * 16;
+  const int kk = cin * 9;
+  for (int i = threadIdx.x; i < kk * 16; i += blockDim.x) {
+    const int k = i / 16, o = i % 16;                       // k = ci * 9 + tap
+    sw[i] = (co0 + o < cout) ? w[(int64_t)(co0 + o) * kk + k] : 0.f;
+  }
+  if (threadIdx.x < 16) sb[threadIdx.x] = (co0 + threadIdx.x < cout) ? b[co0 + threadIdx.x] : 0.f;
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t npix = (int64_t)bn * f * h * wd;
+  if (pix >= npix) return;
   const int x = (int)(pix % wd), yy = (int)((pix / wd) % h);
   const int fr = (int)((pix / ((int64_t)wd * h)) % f);
-  const int s = (int)(pix / ((int64_t)wd * h * f));
-  float acc = b[co];
+  const int smp = (int)(pix / ((int64_t)wd * h * f));
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = sb[o];
   for (int ci = 0; ci < cin; ++ci) {
-    const float* img = sample + (((int64_t)s * cin + ci) * f + fr) * h * wd;
-    const float* wk = w + ((int64_t)co * cin + ci) * 9;
+    const float* img = sample + (((int64_t)smp * cin + ci) * f + fr) * h * wd;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = yy + ky - 1;
-      if (iy < 0 || iy >= h) continue;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = yy + tap / 3 - 1, ix = x + tap % 3 - 1;
+      const float v = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(img + iy * wd + ix) : 0.f;
+      const float4* wr = reinterpret_cast<const float4*>(sw + (ci * 9 + tap) * 16);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = x + kx - 1;
-        if (ix < 0 || ix >= wd) continue;
-        acc += img[iy * wd + ix] * wk[ky * 3 + kx];
+      for (int q = 0; q < 4; ++q) {
+        const float4 ww = wr[q];
+        acc[4 * q] = fmaf(v, ww.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
       }
     }
   }
-  y[idx] = __float2half_rn(acc);
+  __half* dst = y + pix * cout + co0;
+  if (co0 + 16 <= cout) {
+    uint32_t hw8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hw8[i] = pack_f16x2(acc[2 * i], acc[2 * i + 1]);
+    st_global_256(dst, hw8);
+  } else {
+    for (int o = 0; o < 16 && co0 + o < cout; ++o) dst[o] = __float2half_rn(acc[o]);
+  }
 }
 
-// conv_out: x NHWC fp16 [(BN F) H W, Cin] -> y [BN, Cout, F, H, W] fp32 ; one warp per pixel, cout <= 8
-__global__ void conv_out_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                float* __restrict__ y, int bn, int cin, int f, int h, int wd, int cout) {
-  const int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// conv_out: x NHWC fp16 [(BN F) H W, Cin] -> y [BN, Cout, F, H, W] fp32, cout <= 4.  Four lanes per pixel split the input
+// channels in 16-byte vectors (vector c, c+4, ...); weights transposed into shared memory as [tap][cin][4] once per block.
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ y,
+                int bn, int cin, int f, int h, int wd, int cout) {
+  // [tap][part][channels of that part][4 couts] + one float4 of padding per (tap, part): the four lanes of a pixel read
+  // different parts at the same time, the padding puts them on different banks
+  extern __shared__ __align__(16) float swo[];
+  const int nvec = cin / 8;
+  const int vpp = (nvec + 3) / 4;                           // 16-byte vectors per part
+  const int pstride = (vpp * 8 + 1) * 4;                    // floats per (tap, part) block
+  for (int i = threadIdx.x; i < 9 * cin * 4; i += blockDim.x) {
+    const int o = i & 3, c = (i >> 2) % cin, tap = (i >> 2) / cin;
+    const int vb = c >> 3, prt = vb & 3, loc = (vb >> 2) * 8 + (c & 7);
+    swo[(tap * 4 + prt) * pstride + loc * 4 + o] = o < cout ? w[((int64_t)o * cin + c) * 9 + tap] : 0.f;
+  }
+  __syncthreads();
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pix = gid >> 2;
+  const int part = (int)(gid & 3);
   const int64_t npix = (int64_t)bn * f * h * wd;
-  if (pix >= npix) return;
-  const int px = (int)(pix % wd), py = (int)((pix / wd) % h);
-  const int64_t img = pix / ((int64_t)wd * h);   // (bn f)
-  float acc[8];
+  const bool ok = pix < npix;
+  const int px = ok ? (int)(pix % wd) : 0, py = ok ? (int)((pix / wd) % h) : 0;
+  const int64_t img = ok ? pix / ((int64_t)wd * h) : 0;   // (bn f)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ok) {
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+      if (iy < 0 || iy >= h || ix < 0 || ix >= wd) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(x + ((img * h + iy) * wd + ix) * cin);
+      const float4* wt = reinterpret_cast<const float4*>(swo + (size_t)(tap * 4 + part) * pstride);
+      for (int vb = part, j = 0; vb < nvec; vb += 4, ++j) {
+        const uint4 v = __ldg(src + vb);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-  for (int tap = 0; tap < 9; ++tap) {
-    const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
-    if (iy < 0 || iy >= h || ix < 0 || ix >= wd) continue;
-    const __half* src = x + ((img * h + iy) * wd + ix) * cin;
-    for (int c = lane; c < cin; c += 32) {
-      const float v = __half2float(src[c]);
-      for (int o = 0; o < cout; ++o) acc[o] += v * __ldg(w + ((int64_t)o * cin + c) * 9 + tap);
+        for (int t = 0; t < 4; ++t) {
+          const float2 fv = __half22float2(hv[t]);
+          const float4 w0 = wt[j * 8 + 2 * t], w1 = wt[j * 8 + 2 * t + 1];
+          acc[0] = fmaf(fv.x, w0.x, fmaf(fv.y, w1.x, acc[0]));
+          acc[1] = fmaf(fv.x, w0.y, fmaf(fv.y, w1.y, acc[1]));
+          acc[2] = fmaf(fv.x, w0.z, fmaf(fv.y, w1.z, acc[2]));
+          acc[3] = fmaf(fv.x, w0.w, fmaf(fv.y, w1.w, acc[3]));
+        }
+      }
     }
   }
-  for (int o = 0; o < cout; ++o) {
-    float a = acc[o];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-    if (lane == 0) {
-      const int fr = (int)(img % f);
-      const int64_t smp = img / f;
-      y[(((smp * cout + o) * f + fr) * h + py) * wd + px] = a + b[o];
-    }
+  for (int o = 0; o < 4; ++o) {
+    acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+    acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+  }
+  if (ok && part < cout) {     // lane `part` of the pixel's quad writes output channel `part`
+    const int fr = (int)(img % f);
+    const int64_t smp = img / f;
+    const float val = part == 0 ? acc[0] : part == 1 ? acc[1] : part == 2 ? acc[2] : acc[3];
+    y[(((smp * cout + part) * f + fr) * h + py) * wd + px] = val + b[part];
   }
 }
 
@@ -654,8 +702,11 @@ extern "C" int a3d_silu_rows(const float* x, void* y, int64_t rows, int c, int r
 extern "C" int a3d_conv_in(const float* sample, const float* w, const float* b, void* y, int bn, int cin, int f, int h,
                            int wd, int cout, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int64_t total = (int64_t)bn * f * h * wd * cout;
-  conv_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sample, w, b, reinterpret_cast<__half*>(y), bn, cin, f, h, wd, cout);
+  if (cin * 9 > kConvInMaxK) return fail(A3D_EINVAL, "a3d_conv_in: cin <= 8 (got %d)", cin);
+  if (cout % 16 || (reinterpret_cast<uintptr_t>(y) & 31)) return fail(A3D_EINVAL, "a3d_conv_in: cout %% 16 and 32-byte aligned output");
+  const int64_t npix = (int64_t)bn * f * h * wd;
+  dim3 grid((unsigned)((npix + 127) / 128), (unsigned)(cout / 16));
+  conv_in_kernel<<<grid, 128, 0, st>>>(sample, w, b, reinterpret_cast<__half*>(y), bn, cin, f, h, wd, cout);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
@@ -663,9 +714,17 @@ extern "C" int a3d_conv_in(const float* sample, const float* w, const float* b, 
 extern "C" int a3d_conv_out(const void* x, const float* w, const float* b, float* y, int bn, int cin, int f, int h, int wd,
                             int cout, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (cout > 8) return fail(A3D_EINVAL, "a3d_conv_out: cout <= 8");
+  if (cout > 4 || cin % 8) return fail(A3D_EINVAL, "a3d_conv_out: cout <= 4 and cin %% 8 == 0 (got %d, %d)", cout, cin);
   const int64_t npix = (int64_t)bn * f * h * wd;
-  conv_out_kernel<<<(unsigned)((npix * 32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x), w, b, y, bn, cin, f, h, wd, cout);
+  const int vpp = (cin / 8 + 3) / 4;
+  const size_t smem = (size_t)9 * 4 * (vpp * 8 + 1) * 4 * sizeof(float);
+  static size_t max_set = 0;
+  if (smem > 48 * 1024 && smem > max_set) {
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_set = smem;
+  }
+  conv_out_kernel<<<(unsigned)((npix * 4 + 255) / 256), 256, smem, st>>>(reinterpret_cast<const __half*>(x), w, b, y, bn, cin, f, h,
+                                                                        wd, cout);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }

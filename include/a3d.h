@@ -226,6 +226,8 @@ int a3d_deform_backward(const a3d_deform_args* args, const float* dL_dmeans, con
 
 /* debug hook: per-step clock64 timestamps of CTA (0,0,0) of the following head-dim-40 attention launches (NULL = off) */
 int a3d_debug_set_attn_trace(void* device_buffer_1024_int64);
+/* same for the tcgen05 GEMM: per-tile timestamps of CTA 0 (epilogue warp 0 and the MMA-issuing thread) */
+int a3d_debug_set_gemm_trace(void* device_buffer_1024_int64);
 
 #ifdef __cplusplus
 }
