@@ -1,7 +1,10 @@
-"""Dump the per-step timeline (SM clock cycles) of one CTA of the head-dim-40 attention kernel."""
+"""Dump the per-step timeline (SM clock cycles) of one CTA of the head-dim-40 attention kernel (the v3 kernel carries the
+clock64 hooks; v4/v5 share its pipeline but are not instrumented)."""
 import ctypes as C
 import os
 import sys
+
+os.environ.setdefault("A3D_ATTN_VARIANT", "3")
 
 import torch
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-LOG=gpurun_out/run23.log
+LOG=gpurun_out/suite.log
 : > $LOG
 echo "=== full gpu suite" >> $LOG
 timeout 1500 python -m pytest tests -q -m gpu -x --tb=short -p no:cacheprovider 2>&1 | tail -n 25 >> $LOG
