@@ -1748,9 +1748,11 @@ __global__ void attn_simt_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, i
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kFewKeysMax = 8;
 
+template <int D>   // head dim as a template parameter: the channel loops unroll and all Q loads of a row are in flight at once
 __global__ void __launch_bounds__(256)
 attn_fewkeys_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, int64_t os1, int64_t os2, int64_t os3, int64_t os4, int heads,
-                    int d, int dqk, int dv, float scale_log2, int kv_div, int kv_i3_zero, int accumulate, float out_scale) {
+                    int dqk, int dv, float scale_log2, int kv_div, int kv_i3_zero, int accumulate, float out_scale) {
+  constexpr int d = D;
   const int Lq = q.e1 * q.e2, Lk = k.e1 * k.e2;
   const int64_t total = (int64_t)q.e3 * q.e4 * Lq * heads;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1774,6 +1776,7 @@ attn_fewkeys_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, int64_t os1, i
   float sc[kFewKeysMax];
 #pragma unroll
   for (int j = 0; j < kFewKeysMax; ++j) sc[j] = 0.f;
+#pragma unroll
   for (int c = 0; c < d; c += 8) {
     const uint4 qv = *reinterpret_cast<const uint4*>(qp + c);
     const __half2* qh = reinterpret_cast<const __half2*>(&qv);
@@ -1806,6 +1809,7 @@ attn_fewkeys_kernel(ViewDev q, ViewDev k, ViewDev v, __half* out, int64_t os1, i
   const float inv = out_scale / sum;
   __half* op = out + (int64_t)(l % q.e1) * os1 + (int64_t)(l / q.e1) * os2 + (int64_t)(qb % q.e3) * os3 +
                (int64_t)(qb / q.e3) * os4 + h * d;
+#pragma unroll
   for (int c = 0; c < d; c += 8) {
     float acc[8];
 #pragma unroll
@@ -2226,9 +2230,18 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
     ViewDev k{reinterpret_cast<const __half*>(a->k.base), a->k.s1, a->k.s2, a->k.s3, a->k.s4, a->k.e1, a->k.e2, a->k.e3, a->k.e4};
     ViewDev v{reinterpret_cast<const __half*>(a->v.base), a->v.s1, a->v.s2, a->v.s3, a->v.s4, a->v.e1, a->v.e2, a->v.e3, a->v.e4};
     const int64_t total = (int64_t)batches * a->heads * a->q.e1 * a->q.e2;
-    attn_fewkeys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        q, k, v, reinterpret_cast<__half*>(a->out), a->os1, a->os2, a->os3, a->os4, a->heads, d, dqk, dv,
-        a->scale * 1.4426950408889634f, kv_div, a->kv_i3_zero, a->accumulate, a->out_scale == 0.f ? 1.f : a->out_scale);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const float sl2 = a->scale * 1.4426950408889634f, osc = a->out_scale == 0.f ? 1.f : a->out_scale;
+    __half* o = reinterpret_cast<__half*>(a->out);
+    if (d == 40)
+      attn_fewkeys_kernel<40><<<blocks, 256, 0, st>>>(q, k, v, o, a->os1, a->os2, a->os3, a->os4, a->heads, dqk, dv, sl2, kv_div,
+                                                      a->kv_i3_zero, a->accumulate, osc);
+    else if (d == 80)
+      attn_fewkeys_kernel<80><<<blocks, 256, 0, st>>>(q, k, v, o, a->os1, a->os2, a->os3, a->os4, a->heads, dqk, dv, sl2, kv_div,
+                                                      a->kv_i3_zero, a->accumulate, osc);
+    else
+      attn_fewkeys_kernel<160><<<blocks, 256, 0, st>>>(q, k, v, o, a->os1, a->os2, a->os3, a->os4, a->heads, dqk, dv, sl2, kv_div,
+                                                       a->kv_i3_zero, a->accumulate, osc);
     A3D_LAUNCH_CHECK();
     return A3D_OK;
   }
