@@ -202,6 +202,14 @@ class Gaussian4DModel(torch.nn.Module):
             self.global_rot_network, self.global_trans_network = mlp(3), mlp(3)
         self.active_sh_degree = 0
 
+    @classmethod
+    def from_ply(cls, path: str, rot_x_degree: float = 0.0, rot_z_degree: float = 0.0, scale_factor: float = 1.0, **kw):
+        """`load_ply` (gaussian_4d.py:177-306): static gaussians from a 3DGS PLY with the load-time rotate / scale."""
+        from .io import load_gaussian_ply
+        g = load_gaussian_ply(path, rot_x_degree, rot_z_degree, scale_factor)
+        t = lambda k: torch.from_numpy(g[k])
+        return cls(t("_xyz"), t("_scaling"), t("_rotation"), t("_opacity"), t("_features_dc"), **kw)
+
     @property
     def get_opacity(self):
         return torch.sigmoid(self._opacity)

@@ -187,6 +187,64 @@ def load_rotation_fns():
     return ns["build_rotation"], ns["extract_rotation_torch"], ns["euler_angles_to_rotation_matrix"]
 
 
+def run_reference_load_ply(path, rot_x, rot_z, scale):
+    """exec Gaussian4DModel.load_ply (gaussian_4d.py:177-306) out of the file against a fake `self` on the CPU.  `plyfile` is
+    not installed: PlyData.read is stubbed by a thin adapter over the repo's own header parser, so the golden pins the
+    loader's MATH (rotate / scale / quaternion re-orientation, buffer shapes), not the byte parsing -- that is checked
+    separately against struct.unpack in tests/test_io.py."""
+    import types
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from animate3d_b200.io import read_ply_vertices
+    usrc = open(os.path.join(REF, "custom/threestudio-animate3d/geometry/utils.py")).read()
+    utree = ast.parse(usrc)
+    ubody = [n for n in utree.body if isinstance(n, ast.FunctionDef) and n.name in {"build_rotation_np", "extract_rotation_scipy"}]
+    from scipy.spatial.transform import Rotation
+    uns = {"np": np, "R": Rotation}
+    exec(compile(ast.Module(body=ubody, type_ignores=[]), "geometry_utils_np", "exec"), uns)
+
+    class _Prop:
+        def __init__(self, name): self.name = name
+
+    class _Element:
+        def __init__(self, cols): self.cols = cols; self.properties = [_Prop(k) for k in cols]
+        def __getitem__(self, k): return self.cols[k]
+
+    class PlyData:
+        @staticmethod
+        def read(pth):
+            o = types.SimpleNamespace(); o.elements = [_Element(read_ply_vertices(pth))]; return o
+
+    class _TorchCpu:          # torch with device="cuda" dropped
+        float = torch.float
+        @staticmethod
+        def tensor(x, dtype=None, device=None): return torch.tensor(x, dtype=dtype)
+        @staticmethod
+        def zeros(shape, device=None): return torch.zeros(shape)
+
+    src = open(os.path.join(REF, "custom/threestudio-animate3d/geometry/gaussian_4d.py")).read()
+    fn = None
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == "Gaussian4DModel":
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == "load_ply":
+                    fn = sub
+    ns = {"np": np, "torch": _TorchCpu, "nn": nn, "PlyData": PlyData, "build_rotation_np": uns["build_rotation_np"],
+          "extract_rotation_scipy": uns["extract_rotation_scipy"]}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "gaussian_4d_load_ply", "exec"), ns)
+
+    class FakeSelf:
+        def __init__(self):
+            self.cfg = types.SimpleNamespace(load_ply_cfg=types.SimpleNamespace(rot_x_degree=rot_x, rot_z_degree=rot_z, scale_factor=scale))
+            self.max_sh_degree = 0
+            for k in ("_xyz", "_features_dc", "_features_rest", "_opacity"):
+                setattr(self, k, None)
+        def register_buffer(self, name, t): setattr(self, name, t)
+    me = FakeSelf()
+    ns["load_ply"](me, path)
+    return {k: getattr(me, k).detach().clone() for k in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation")}
+
+
 def attn_weights(attn, prefix):
     return {f"{prefix}.to_q.weight": attn.to_q.weight.detach().clone(),
             f"{prefix}.to_k.weight": attn.to_k.weight.detach().clone(),
@@ -297,6 +355,20 @@ def main():
     assert (tr <= 0).sum() > 20 and (tr > 0).sum() > 20
     torch.save({"quats": quats, "angles": angles, "mats": mats, "rmats": rmats, "rotated": rotated},
                os.path.join(OUT, "ref_rotation.pt"))
+
+    # 3DGS PLY + the loader's rotate / scale step (gaussian_4d.py:177-306); the PLY itself is committed as a fixture
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from animate3d_b200.io import write_gaussian_ply
+    rng = np.random.default_rng(5)
+    n = 300
+    ply = os.path.join(OUT, "ref_gaussians.ply")
+    write_gaussian_ply(ply, rng.normal(size=(n, 3)), rng.normal(size=(n, 3)), rng.normal(size=(n, 1)),
+                       rng.normal(size=(n, 3)) * 0.5 - 3.0, rng.normal(size=(n, 4)))
+    ply_out = {}
+    for cfg in ((0.0, 0.0, 1.0), (-90.0, 30.0, 1.7), (45.0, -120.0, 0.4)):
+        ply_out[cfg] = run_reference_load_ply(ply, *cfg)
+    torch.save(ply_out, os.path.join(OUT, "ref_ply.pt"))
 
     get_camera = load_camera_fns()
     cam = {n: get_camera(n) for n in (1, 4, 8)}
