@@ -245,6 +245,78 @@ def run_reference_load_ply(path, rot_x, rot_z, scale):
     return {k: getattr(me, k).detach().clone() for k in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation")}
 
 
+def fake_unet_eps(lat, ts, ehs, cam, img):
+    """Deterministic stand-in for the UNet in the guidance golden (depends on every conditioning input).  tests/test_guidance.py
+    carries the same function."""
+    v = lambda x: x.reshape(-1, 1, 1, 1, 1)
+    return (0.1 * lat * v(torch.cos(ts.float() / 1000.0)) + 0.01 * v(ehs.float().mean((1, 2))) + 0.02 * v(cam.float().sum(1))
+            + 0.03 * v(img.float().mean(1)) + 0.05 * torch.sin(3.0 * lat))
+
+
+def run_reference_recon_loss():
+    """exec AnimateMVDiffusionGuidance.compute_mvdream_recon_loss + get_camera_cond + normalize_camera out of
+    animatemv_guidance.py (391-513, 347-363, 40-52) against a fake `self`: the UNet is `fake_unet_eps`, the scheduler a
+    minimal restatement of diffusers' DDIMScheduler.add_noise / step(...).pred_original_sample (not installed)."""
+    import numpy as np
+    from einops import rearrange
+    src = open(os.path.join(REF, "custom/threestudio-animate3d/guidance/animatemv_guidance.py")).read()
+    tree = ast.parse(src)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "normalize_camera"]
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "AnimateMVDiffusionGuidance":
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name in ("compute_mvdream_recon_loss", "get_camera_cond"):
+                    sub.decorator_list = []
+                    sub.returns = None
+                    for a in sub.args.args + sub.args.kwonlyargs:
+                        a.annotation = None
+                    body.append(sub)
+    ns = {"torch": torch, "np": np, "F": F, "rearrange": rearrange}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "animatemv_guidance_recon", "exec"), ns)
+
+    betas = torch.linspace(0.00085, 0.012, 1000, dtype=torch.float32)
+    acp = torch.cumprod(1.0 - betas, 0)
+
+    class Sched:
+        def add_noise(self, x, noise, t):
+            a = acp[t]
+            sa, sb = a.sqrt().flatten(), (1 - a).sqrt().flatten()
+            while sa.ndim < x.ndim:
+                sa, sb = sa.unsqueeze(-1), sb.unsqueeze(-1)
+            return sa * x + sb * noise
+        def step(self, eps, t, x):
+            a = acp[t]
+            return SimpleNamespace(pred_original_sample=(x - (1 - a) ** 0.5 * eps) / a ** 0.5)
+
+    B, n, f = 1, 2, 3
+    g = torch.Generator().manual_seed(123)
+    latents = torch.randn(B * n * f, 4, 6, 6, generator=g)
+    t = torch.tensor([137])
+    text = torch.randn(2 * B * n, 77, 16, generator=g)
+    c2w = torch.randn(B * n * f, 4, 4, generator=g)
+    img = torch.randn(B * n, 32, generator=g)
+    out = {}
+    for rescale in (0.5, 0.0):
+        me = SimpleNamespace(cfg=SimpleNamespace(n_view=n, n_frame=f, guidance_scale=5.0, recon_std_rescale=rescale,
+                                                 i2v_cond_time_zero=False, view_dependent_prompting=False,
+                                                 camera_condition_type="rotation"),
+                             scheduler=Sched())
+        me.get_camera_cond = lambda cam, fovy=None, _me=me: ns["get_camera_cond"](_me, cam, fovy)
+        me.forward_unet = lambda lat, ts, encoder_hidden_states, camera, i2v_cond_time_zero, added_cond_kwargs: fake_unet_eps(
+            lat, ts, encoder_hidden_states, camera, added_cond_kwargs["image_embeds"])
+        prompt = SimpleNamespace(get_text_embeddings=lambda *a, **k: text, use_perp_neg=False)
+        zeros = torch.zeros(B * n * f)
+        torch.manual_seed(777)
+        lat_in = latents.clone().requires_grad_(True)
+        loss, aux = ns["compute_mvdream_recon_loss"](me, lat_in, t, prompt, zeros, zeros, zeros, camera=c2w.clone(),
+                                                     image_embeds=img.clone())
+        loss.backward()
+        out[rescale] = {"loss": loss.detach(), "grad": lat_in.grad.clone(), "latents_noisy": aux["latents_noisy"].clone(),
+                        "noise_pred": aux["noise_pred"].clone(), "latents_recon": aux["latents_recon"].detach().clone()}
+    torch.save({"latents": latents, "t": t, "text": text, "c2w": c2w, "img": img, "n": n, "f": f, "seed": 777, "out": out},
+               os.path.join(OUT, "ref_guidance.pt"))
+
+
 def attn_weights(attn, prefix):
     return {f"{prefix}.to_q.weight": attn.to_q.weight.detach().clone(),
             f"{prefix}.to_k.weight": attn.to_k.weight.detach().clone(),
@@ -369,6 +441,8 @@ def main():
     for cfg in ((0.0, 0.0, 1.0), (-90.0, 30.0, 1.7), (45.0, -120.0, 0.4)):
         ply_out[cfg] = run_reference_load_ply(ply, *cfg)
     torch.save(ply_out, os.path.join(OUT, "ref_ply.pt"))
+
+    run_reference_recon_loss()
 
     get_camera = load_camera_fns()
     cam = {n: get_camera(n) for n in (1, 4, 8)}
