@@ -317,6 +317,46 @@ def run_reference_recon_loss():
                os.path.join(OUT, "ref_guidance.pt"))
 
 
+def run_reference_cam_info():
+    """exec convert_pose / get_projection_matrix_gaussian / get_cam_info_gaussian (threestudio/utils/ops.py:305-359) on the
+    CPU: `.cuda()` calls are dropped and the `device="cuda"` default becomes "cpu" in the AST, nothing else changes."""
+    src = open(os.path.join(REF, "threestudio/utils/ops.py")).read()
+    want = {"convert_pose", "get_projection_matrix_gaussian", "get_cam_info_gaussian"}
+    body = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want]
+
+    class NoCuda(ast.NodeTransformer):
+        def visit_Call(self, node):
+            self.generic_visit(node)
+            if isinstance(node.func, ast.Attribute) and node.func.attr == "cuda" and not node.args:
+                return node.func.value
+            return node
+
+        def visit_FunctionDef(self, node):
+            self.generic_visit(node)
+            node.args.defaults = [ast.Constant("cpu") if isinstance(d, ast.Constant) and d.value == "cuda" else d
+                                  for d in node.args.defaults]
+            return node
+    mod = ast.fix_missing_locations(NoCuda().visit(ast.Module(body=body, type_ignores=[])))
+    ns = {"torch": torch, "math": math}
+    exec(compile(mod, "threestudio_ops_cam", "exec"), ns)
+    g = torch.Generator().manual_seed(17)
+    cams = []
+    for i in range(6):
+        q = torch.randn(4, generator=g)
+        q = q / q.norm()
+        r, x, y, z = q.tolist()
+        rot = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)],
+                            [2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)],
+                            [2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)]])
+        c2w = torch.eye(4)
+        c2w[:3, :3] = rot
+        c2w[:3, 3] = torch.randn(3, generator=g) * 2
+        fovx, fovy = 0.6 + 0.1 * i, 0.5 + 0.07 * i
+        wv, full, center = ns["get_cam_info_gaussian"](c2w.clone(), fovx, fovy, 0.1, 100.0)
+        cams.append({"c2w": c2w, "fovx": fovx, "fovy": fovy, "wv": wv.clone(), "full": full.clone(), "center": center.clone()})
+    torch.save(cams, os.path.join(OUT, "ref_cam_info.pt"))
+
+
 def attn_weights(attn, prefix):
     return {f"{prefix}.to_q.weight": attn.to_q.weight.detach().clone(),
             f"{prefix}.to_k.weight": attn.to_k.weight.detach().clone(),
@@ -443,6 +483,7 @@ def main():
     torch.save(ply_out, os.path.join(OUT, "ref_ply.pt"))
 
     run_reference_recon_loss()
+    run_reference_cam_info()
 
     get_camera = load_camera_fns()
     cam = {n: get_camera(n) for n in (1, 4, 8)}

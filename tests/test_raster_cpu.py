@@ -100,3 +100,26 @@ def test_backward_matches_autograd_through_oracle(harness, P, H, W, seed):
         scale = np.abs(ref).max() + 1e-12
         err = np.abs(mine - ref).max() / scale
         assert err < 2e-3, f"grad {name}: max err / max ref = {err:.3e}"
+
+
+def test_cam_info_matches_reference_source(golden_dir):
+    """Camera -> (world_view, full_proj, centre) of threestudio/utils/ops.py:305-359: the oracle and the product's batched
+    version against outputs of the reference functions themselves."""
+    import os
+
+    import torch
+
+    from animate3d_b200.renderer import get_cam_info_gaussian as batched
+    from oracle import raster_oracle as R
+    cams = torch.load(os.path.join(golden_dir, "ref_cam_info.pt"), weights_only=False)
+    for c in cams:
+        wv, full, centre = R.get_cam_info_gaussian(c["c2w"], c["fovx"], c["fovy"], 0.1, 100.0)
+        torch.testing.assert_close(wv, c["wv"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(full, c["full"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(centre, c["center"], rtol=1e-5, atol=1e-6)
+    c2w = torch.stack([c["c2w"] for c in cams])
+    wv, full, centre, tx, ty = batched(c2w, torch.tensor([c["fovx"] for c in cams]), torch.tensor([c["fovy"] for c in cams]))
+    torch.testing.assert_close(wv, torch.stack([c["wv"] for c in cams]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(full, torch.stack([c["full"] for c in cams]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(centre, torch.stack([c["center"] for c in cams]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(tx, torch.tan(torch.tensor([c["fovx"] for c in cams]) * 0.5))
