@@ -89,14 +89,15 @@ class ClockSampler:
 
 def best_cpu_threads(sd):
     """Pick the torch thread count that runs the oracle fastest on this host (on a 128-core box all-cores is ~15x SLOWER
-    than 16-32 threads for these layer sizes); the baseline is reported at its best setting."""
+    than 16-32 threads for these layer sizes); the baseline is reported at its best setting.  Probes 8 / 16 / 32 threads on
+    a single-frame forward (about a second each) -- never the all-cores setting, which alone can take minutes."""
     import torch
     from oracle import unet_oracle as O
     ocfg = O.UNetConfig(num_views=1, num_frames=1)
     sample, text, camera, img = O.synthetic_inputs(ocfg, 1, 1, 1, 0)
     ncpu = os.cpu_count() or 1
     best, best_t = 1, float("inf")
-    for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+    for n in sorted({min(ncpu, c) for c in (8, 16, 32)}):
         torch.set_num_threads(n)
         with torch.no_grad():
             t0 = time.perf_counter()
@@ -104,7 +105,7 @@ def best_cpu_threads(sd):
             dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = n, dt
-        if dt > 3 * best_t:
+        if dt > 1.5 * best_t:
             break
     torch.set_num_threads(best)
     return best
@@ -117,6 +118,7 @@ def cpu_oracle_sample(repeats=1):
     from animate3d_b200.unet_config import UNetConfig
     from oracle import unet_oracle as O
     ocfg = O.UNetConfig(num_views=1, num_frames=4)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))   # never run the oracle (or build its weights) on all cores
     sd = O.make_state_dict(ocfg, 0)
     cores = best_cpu_threads(sd)
     sample, text, camera, img = O.synthetic_inputs(ocfg, 1, 1, 4, 0)
@@ -140,6 +142,7 @@ def run_reference(args, rank, world):
     from animate3d_b200.unet_config import UNetConfig
     nf = 1 if os.environ.get("A3D_BENCH_TINY") else 4
     ocfg = O.UNetConfig(num_views=1, num_frames=nf)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))   # never run the oracle (or build its weights) on all cores
     sd = O.make_state_dict(ocfg, 0)
     cores = best_cpu_threads(sd)
     sample, text, camera, img = O.synthetic_inputs(ocfg, 1, 1, nf, 0)
