@@ -25,3 +25,17 @@ def random_state_dict(cfg: UNetConfig, seed: int = 0, device="cuda", std: float 
         else:
             sd[k] = torch.randn(shape, generator=g, device=device) * std
     return sd
+
+
+def load_unet_checkpoint(unet, path: str, map_location="cpu"):
+    """inference.py:213-223: `torch.load`, unwrap an optional "state_dict" entry, `load_state_dict(strict=False)` and the
+    reference's two invariants -- nothing unexpected, and either the full model (0 missing) or the released motion-module
+    checkpoint (exactly the 726 non-motion keys missing).  Returns (missing, unexpected)."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=True)
+    sd = ckpt["state_dict"] if isinstance(ckpt, dict) and "state_dict" in ckpt else ckpt
+    missing, unexpected = unet.load_state_dict(sd, strict=False)
+    if unexpected:
+        raise ValueError(f"{path}: {len(unexpected)} unexpected keys (file is broken), e.g. {unexpected[:3]}")
+    if len(missing) not in (0, 726):
+        raise ValueError(f"{path}: {len(missing)} missing keys; expected 0 (full model) or 726 (motion modules only)")
+    return missing, unexpected
