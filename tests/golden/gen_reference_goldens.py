@@ -357,6 +357,72 @@ def run_reference_cam_info():
     torch.save(cams, os.path.join(OUT, "ref_cam_info.pt"))
 
 
+def run_reference_arap():
+    """exec produce_edge_matrix_nfmt / cal_connectivity_from_points / estimate_rotation / cal_arap_error out of
+    systems/util.py on the CPU: `.cuda()` / `.to(device)` dropped in the AST, pytorch3d.ops served by a brute-force KNN with
+    the published knn_points contract, np.random.choice replaced by a recorded index draw."""
+    import numpy as np
+    src = open(os.path.join(REF, "custom/threestudio-animate3d/systems/util.py")).read()
+    want = {"produce_edge_matrix_nfmt", "cal_connectivity_from_points", "estimate_rotation", "cal_arap_error"}
+    body = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want]
+    for fn in body:
+        fn.decorator_list = []
+
+    class NoCuda(ast.NodeTransformer):
+        def visit_Call(self, node):
+            self.generic_visit(node)
+            if isinstance(node.func, ast.Attribute) and node.func.attr == "cuda" and not node.args:
+                return node.func.value
+            if isinstance(node.func, ast.Attribute) and node.func.attr == "to" and len(node.args) == 1 and \
+                    isinstance(node.args[0], ast.Name) and node.args[0].id == "device":
+                return node.func.value
+            return node
+    mod = ast.fix_missing_locations(NoCuda().visit(ast.Module(body=body, type_ignores=[])))
+
+    def knn_points(p1, p2, l1, l2, K):
+        d2 = ((p1[:, :, None, :] - p2[:, None, :, :]) ** 2).sum(-1)
+        dist, idx = torch.sort(d2, dim=2, stable=True)
+        return SimpleNamespace(dists=dist[:, :, :K], idx=idx[:, :, :K])
+
+    def knn_gather(x, idx):
+        return torch.stack([x[b][idx[b]] for b in range(x.shape[0])])
+    drawn = {}
+
+    class FakeRandom:
+        @staticmethod
+        def choice(n, k):
+            r = np.random.RandomState(99).choice(n, k)
+            drawn["idx"] = torch.from_numpy(r).long()
+            return r
+    fake_np = SimpleNamespace(random=FakeRandom)
+    ns = {"torch": torch, "np": fake_np, "svd": torch.svd,
+          "pytorch3d": SimpleNamespace(ops=SimpleNamespace(knn_points=knn_points, knn_gather=knn_gather))}
+    exec(compile(mod, "systems_util_arap", "exec"), ns)
+    g = torch.Generator().manual_seed(41)
+    nt, nv, K = 4, 120, 3                        # arap_K = 3 = least_edge_num in every shipped config
+    base = torch.rand(nv, 3, generator=g)
+    seq = [base]
+    for t in range(1, nt):                       # smooth non-rigid motion: rotation about z growing with height + noise
+        ang = 0.15 * t * (0.5 + base[:, 2])
+        rot = torch.stack([torch.cos(ang) * base[:, 0] - torch.sin(ang) * base[:, 1],
+                           torch.sin(ang) * base[:, 0] + torch.cos(ang) * base[:, 1], base[:, 2]], 1)
+        seq.append(rot + 0.01 * torch.randn(nv, 3, generator=g))
+    nodes = torch.stack(seq)
+    nodes[:, :5] = nodes[0:1, :5]                # a few nodes that never move (the S = 0 branch)
+    # as called by systems/animate3d.py:236-241: graph from frame 0 only, error with weight=None (indicator weights)
+    ii, jj, nn, weight = ns["cal_connectivity_from_points"](nodes[:1].clone(), radius=0.01, K=K)
+    rot = ns["estimate_rotation"](nodes[0], nodes[2], ii, jj, nn, K=K, weight=weight)
+    lat = nodes.clone().requires_grad_(True)
+    err_all = ns["cal_arap_error"](lat, ii, jj, nn, K=K, sample_num=512)
+    err_all.backward()
+    lat2 = nodes.clone().requires_grad_(True)
+    err_sub = ns["cal_arap_error"](lat2, ii, jj, nn, K=K, sample_num=50)
+    err_sub.backward()
+    torch.save({"nodes": nodes, "K": K, "radius": 0.01, "ii": ii, "jj": jj, "nn": nn, "weight": weight, "rot_0_2": rot,
+                "err_all": err_all.detach(), "grad_all": lat.grad.clone(), "sample_idx": drawn["idx"],
+                "err_sub": err_sub.detach(), "grad_sub": lat2.grad.clone()}, os.path.join(OUT, "ref_arap.pt"))
+
+
 def attn_weights(attn, prefix):
     return {f"{prefix}.to_q.weight": attn.to_q.weight.detach().clone(),
             f"{prefix}.to_k.weight": attn.to_k.weight.detach().clone(),
@@ -484,6 +550,7 @@ def main():
 
     run_reference_recon_loss()
     run_reference_cam_info()
+    run_reference_arap()
 
     get_camera = load_camera_fns()
     cam = {n: get_camera(n) for n in (1, 4, 8)}
