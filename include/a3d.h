@@ -71,6 +71,11 @@ typedef struct a3d_gemm_args {
   int impl;                   /* A3D_GEMM_* */
 } a3d_gemm_args;
 
+/* Replaces every Linear / Conv2d(3x3) the reference's forward issues through torch: ResnetBlock2D conv1/conv2/
+ * time_emb_proj/conv_shortcut, Down/Upsample2D convs, Transformer2DModel proj_in/proj_out + BasicTransformerBlock FF
+ * (GEGLU) (diffusers 0.28, reached from animatediff/models/unet_motion_mv_model.py:768-859), and the processors'
+ * to_q/to_k/to_v/to_out + *_i2v / *_ip / *_sp projections (animatediff/models/attention_processor.py:211-231, 383-403,
+ * 425-441, 600-655, 686-717), with their bias, residual, positional-table and layout epilogues fused. */
 int a3d_gemm(const a3d_gemm_args* args, void* stream);
 
 /* ---------------------------------------------------------------- fused attention (tcgen05) ------------------ */
@@ -102,33 +107,46 @@ typedef struct a3d_attn_args {
   int impl;                 /* A3D_GEMM_AUTO / _TCGEN05 / _SIMT */
 } a3d_attn_args;
 
+/* Replaces the xformers.ops.memory_efficient_attention calls of the processors together with the einops regroups around
+ * them: animatediff/models/attention_processor.py:233 (text keys) and 268 (IP-adapter image keys, accumulated with
+ * `scale`), 405 (cross-view self-attention) and 416 (I2V branch, frame-0 keys: kv_i3_zero), 656 and 691 (spatio-temporal
+ * processor's cross-view / image branches). */
 int a3d_attention(const a3d_attn_args* args, void* stream);
 
-/* Temporal attention over F frames for every (pixel, head): qkv [P, F, 3*C] fp16 (q | k | v), out [P, F, C]. */
+/* Temporal attention over F frames for every (pixel, head): qkv [P, F, 3*C] fp16 (q | k | v), out [P, F, C].
+ * Replaces the attention of the motion modules' temporal transformer blocks (diffusers TransformerTemporalModel reached
+ * from unet_motion_mv_model.py:790-836) and the temporal branch of attention_processor.py:541-723 (line 103's call). */
 int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, int heads, int d, float scale, void* stream);
 
 /* ---------------------------------------------------------------- normalisation / elementwise ---------------- */
-/* GroupNorm over (rows_per_sample x C/groups) per sample, NHWC fp16.  x = concat(x1[C1], x2[C2]) along channels
+/* Replaces nn.GroupNorm (+ SiLU) of ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, TransformerTemporalModel.norm
+ * (over frames) and conv_norm_out + conv_act (unet_motion_mv_model.py:262-266, 855-857).
+ * GroupNorm over (rows_per_sample x C/groups) per sample, NHWC fp16.  x = concat(x1[C1], x2[C2]) along channels
  * (x2 may be NULL).  Optional SiLU.  Output rows may be permuted (perm_a, perm_b as in a3d_gemm). */
 int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* y,
                    int64_t samples, int64_t rows_per_sample, int groups, float eps, int silu, int64_t perm_a,
                    int64_t perm_b, float* ws_stats, void* stream);
-/* LayerNorm over C per row. */
+/* LayerNorm over C per row: BasicTransformerBlock.norm1/2/3 of the spatial and temporal transformers (diffusers). */
 int a3d_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int c, float eps,
                    void* stream);
-/* nearest x2 upsample NHWC */
+/* nearest x2 upsample NHWC: Upsample2D's F.interpolate in the up blocks (unet_motion_mv_model.py:838-850) */
 int a3d_upsample2x(const void* x, void* y, int64_t n, int h, int w, int c, void* stream);
 /* y[r, :] = silu(x[r / rep, :]) as fp16 (time-embedding broadcast for the time_emb_proj GEMM) */
 int a3d_silu_rows(const float* x, void* y, int64_t rows, int c, int rep, void* stream);
-/* conv_in: sample [BN, Cin, F, H, W] (fp32) -> NHWC fp16 [(BN F), H, W, Cout], 3x3 pad 1; w [Cout, Cin, 3, 3] fp32 */
+/* conv_in: sample [BN, Cin, F, H, W] (fp32) -> NHWC fp16 [(BN F), H, W, Cout], 3x3 pad 1; w [Cout, Cin, 3, 3] fp32.
+ * Replaces the permute/reshape + self.conv_in of unet_motion_mv_model.py:765-768. */
 int a3d_conv_in(const float* sample, const float* w, const float* b, void* y, int bn, int cin, int f, int h, int wd,
                 int cout, void* stream);
-/* conv_out: NHWC fp16 [(BN F), H, W, Cin] -> [BN, Cout, F, H, W] fp32 */
+/* conv_out: NHWC fp16 [(BN F), H, W, Cin] -> [BN, Cout, F, H, W] fp32.  Replaces self.conv_out + the reshape/permute back
+ * to [B, C, F, H, W] of unet_motion_mv_model.py:857-862. */
 int a3d_conv_out(const void* x, const float* w, const float* b, float* y, int bn, int cin, int f, int h, int wd,
                  int cout, void* stream);
-/* sinusoidal timestep projection + 2-layer MLP inputs: out[r, :] = [cos(t_r f_i), sin(t_r f_i)] fp32, dim = 2*half */
+/* sinusoidal timestep projection: out[r, :] = [cos(t_r f_i), sin(t_r f_i)] fp32, dim = 2*half -- diffusers `Timesteps`
+ * (flip_sin_to_cos=True, freq_shift=0) as called at unet_motion_mv_model.py:723, 734 (self.time_proj) */
 int a3d_timestep_proj(const float* t, float* out, int rows, int half, void* stream);
-/* small fp32 linear: y[M,N] = act(x[M,K]) W[N,K]^T + b  (act: 0 none, 1 silu);  add: y += previous y when accumulate */
+/* small fp32 linear: y[M,N] = act(x[M,K]) W[N,K]^T + b  (act: 0 none, 1 silu);  add: y += previous y when accumulate.
+ * The two TimestepEmbedding MLPs (time_embedding, camera_embedding; unet_motion_mv_model.py:730, 737, 742) and the IP-adapter
+ * ImageProjection (encoder_hid_proj, 754-763). */
 int a3d_linear_f32(const float* x, const float* w, const float* b, float* y, int m, int n, int k, int act_in,
                    int accumulate, void* stream);
 /* fp32 -> fp16 cast with optional LayerNorm-free copy (utility) */
