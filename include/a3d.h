@@ -242,6 +242,20 @@ int a3d_deform_featmean(const a3d_deform_args* args, float* featmean, void* stre
 int a3d_deform_backward(const a3d_deform_args* args, const float* dL_dmeans, const float* dL_dscales, const float* dL_drotations,
                         void* stream);
 
+/* ---------------------------------------------------------------- ARAP regulariser -------------- */
+/* K nearest neighbours of every point among the same points, self excluded, squared distances ascending, ties by index:
+ * pytorch3d.ops.knn_points(p, p, K=K+1)[..., 1:] as used by cal_connectivity_from_points
+ * (custom/threestudio-animate3d/systems/util.py:79-82).  nbr [n,K] int32, dist2 [n,K]; K <= 8. */
+int a3d_knn_graph(const float* points, int n, int K, int32_t* nbr, float* dist2, void* stream);
+/* cal_arap_error (util.py:183-215) with estimate_rotation (138-173) fused, all frames in one launch:
+ *   err = sum_{t>=1} sum_{i in sample} sum_n w[i,n] | e_in(t) - R_i(t) e_in(0) |^2,   e_in(t) = x_t[i] - x_t[nbr[i,n]],
+ * R_i(t) = the weighted Procrustes rotation of the node's frame-0 edges onto its frame-t edges (no gradient through R).
+ * nodes [Nt,Nv,3]; nbr [Nv,K] (-1 = no edge); weight [Nv,K] or NULL (1 on existing edges, the reference's call);
+ * sample [Ns] node indices or NULL (all nodes).  err: device scalar; grad [Nt,Nv,3] = d err / d nodes or NULL.  Both are
+ * zeroed here.  STATUS: arithmetic validated on the CPU (tests/test_arap_cpu.py); GPU run pending. */
+int a3d_arap(const float* nodes, int Nt, int Nv, const int32_t* nbr, int K, const float* weight, const int32_t* sample, int Ns,
+             float* err, float* grad, void* stream);
+
 /* debug hook: per-step clock64 timestamps of CTA (0,0,0) of the following head-dim-40 attention launches (NULL = off) */
 int a3d_debug_set_attn_trace(void* device_buffer_1024_int64);
 /* same for the tcgen05 GEMM: per-tile timestamps of CTA 0 (epilogue warp 0 and the MMA-issuing thread) */

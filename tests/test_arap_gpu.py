@@ -1,0 +1,54 @@
+"""ARAP CUDA wrapper (a3d_knn_graph / a3d_arap) against the reference goldens and the oracle.  The shared arithmetic is
+already validated on the CPU (tests/test_arap_cpu.py); this wrapper was written after the round's GPU budget was spent, so
+the check runs in a SUBPROCESS (a fault cannot poison this process's CUDA context) and is a non-strict xfail until it has
+been seen green on hardware."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = textwrap.dedent("""
+    import os, sys, torch
+    sys.path.insert(0, %r)
+    from animate3d_b200 import arap as P
+    from oracle import arap_oracle as A
+    d = torch.load(os.path.join(%r, "tests", "golden", "ref_arap.pt"), weights_only=False)
+    nodes, K = d["nodes"].cuda(), d["K"]
+    ii, jj, nn, w = P.cal_connectivity_from_points(nodes[:1], radius=d["radius"], K=K)
+    assert torch.equal(ii.cpu(), d["ii"]) and torch.equal(jj.cpu(), d["jj"]) and torch.equal(nn.cpu(), d["nn"]), "graph indices"
+    torch.testing.assert_close(w.cpu(), d["weight"], rtol=1e-5, atol=1e-6)
+    for key, idx in (("all", None), ("sub", d["sample_idx"])):
+        x = nodes.clone().requires_grad_(True)
+        e = P.cal_arap_error(x, ii, jj, nn, K=K, sample_idx=idx)
+        e.backward()
+        want_e, want_g = d["err_" + key], d["grad_" + key]
+        assert abs(float(e) - float(want_e)) <= 2e-4 * abs(float(want_e)) + 1e-7, (key, float(e), float(want_e))
+        assert (x.grad.cpu() - want_g).abs().max() <= 2e-3 * want_g.abs().max() + 1e-7, key
+    # a larger random problem against the oracle (CPU): 3000 nodes, 5 frames, K = 3
+    g = torch.Generator().manual_seed(4)
+    base = torch.rand(3000, 3, generator=g)
+    seq = torch.stack([base + 0.02 * t * torch.randn(3000, 3, generator=g) for t in range(5)])
+    oi, oj, on, ow = A.connectivity_from_points(seq[:1], radius=0.01, K=3)
+    ii, jj, nn, w = P.cal_connectivity_from_points(seq[:1].cuda(), radius=0.01, K=3)
+    assert torch.equal(ii.cpu(), oi) and torch.equal(jj.cpu(), oj) and torch.equal(nn.cpu(), on), "graph indices (3000)"
+    xo = seq.clone().requires_grad_(True)
+    eo = A.arap_error(xo, oi, oj, on, 3)
+    eo.backward()
+    xg = seq.cuda().requires_grad_(True)
+    eg = P.cal_arap_error(xg, ii, jj, nn, K=3, sample_num=10 ** 9)
+    eg.backward()
+    assert abs(float(eg) - float(eo)) <= 5e-4 * abs(float(eo)), (float(eg), float(eo))
+    assert (xg.grad.cpu() - xo.grad).abs().max() <= 5e-3 * xo.grad.abs().max()
+    print("ARAP_GPU_OK")
+""") % (ROOT, ROOT)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="CUDA wrapper not yet run on hardware (round-1 GPU budget spent); arithmetic is CPU-validated")
+def test_arap_cuda_wrapper_in_subprocess():
+    r = subprocess.run([sys.executable, "-c", SCRIPT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ARAP_GPU_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
