@@ -168,6 +168,19 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
+def mufu_note(att_flops, att_ms, clocks):
+    """The pipe that actually bounds this kernel at head_dim 40: one ex2 per score at 8 cycles per
+    warp instruction per SM sub-partition plus one F2FP per score pair at 4 (profiles/r01_pipes_ubench.txt)."""
+    try:
+        scores = att_flops / (4.0 * 40.0)                       # 4 * d FLOP per (query, key) pair
+        cycles = (scores / 32.0 * 8.0 + scores / 64.0 * 4.0) / (148 * 4)
+        mhz = float(clocks.get("sm_mhz") or 1965.0)
+        floor_ms = cycles / (mhz * 1e3)
+        return {"floor_ms": floor_ms, "frac_of_floor": floor_ms / att_ms, "sm_mhz_used": mhz}
+    except Exception as e:                                      # never let a diagnostic field break the bench line
+        return {"error": str(e)}
+
+
 def time_attention_l0(torch, iters=10):
     """The dominant kernel alone: level-0 cross-view attention launch of the CFG step (32 batches x 8 heads, L=4096, d=40)."""
     from animate3d_b200 import ops
@@ -314,7 +327,8 @@ def run_native(args, rank, world, local_rank):
                    "cuda_graph": bool(model.use_cuda_graph)},
         "roofline": {"bound": "tensor", "kernel": "a3d_attention head_dim 40 (fused cross-view attention, L=4096, 32 batches x 8 heads)",
                      "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf, "traffic": traffic,
-                     "ms_per_launch": att_ms, "flop_per_launch": att_flops, "peak_source": peak_src},
+                     "ms_per_launch": att_ms, "flop_per_launch": att_flops, "peak_source": peak_src,
+                     "mufu": mufu_note(att_flops, att_ms, clocks)},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": (model.launches_per_forward + 1) * args.steps,
