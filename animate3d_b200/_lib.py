@@ -73,6 +73,7 @@ def load(require_gpu: bool = True) -> C.CDLL:
                            "(there is no CPU / PyTorch fallback for the hot path)")
         lib = C.CDLL(LIB_PATH)
         lib.a3d_last_error.restype = C.c_char_p
+        lib.a3d_group_norm_ws_bytes.restype = C.c_size_t
         lib.a3d_raster_workspace_bytes.restype = C.c_size_t
         lib.a3d_raster_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
         _lib = lib

@@ -22,37 +22,67 @@ __device__ __forceinline__ int64_t perm_row2(int64_t m, int64_t a, int64_t b) {
 // rows per block (chunk) is chosen on the host: 128 when that still yields >= ~4 blocks per SM, fewer rows otherwise (the
 // over-frames GroupNorm of the motion modules has only B*Nv = 8 samples)
 
+// Statistics are DETERMINISTIC and cancellation-free: no atomics anywhere.  Every thread accumulates its 8 channels around a
+// per-channel pivot (the first value it sees), turns them into (n, mean, M2) triples, and triples are merged with Chan's
+// parallel-variance formula in a FIXED order: channels -> group slot inside the thread, a shared-memory tree over the
+// block's row lanes, a short serial merge over the vectors of a group, one (n, mean, M2) partial per (sample, chunk, group)
+// in global memory, and finally one warp per (sample, group) folding the chunk partials (strided, then a shuffle tree).
+struct Moments {
+  float n, mean, m2;
+};
+
+__device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
+  if (b.n == 0.f) return a;
+  if (a.n == 0.f) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  const float d = b.mean - a.mean, w = b.n / r.n;
+  r.mean = fmaf(d, w, a.mean);
+  r.m2 = a.m2 + b.m2 + d * d * a.n * w;
+  return r;
+}
+
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int rows_per_sample, int groups,
-                int rows_par, int chunk_rows, float* __restrict__ stats) {
-  extern __shared__ float sm[];  // [2 * groups]
+                int rows_par, int chunk_rows, float* __restrict__ partials) {
+  extern __shared__ float sm[];  // [rows_par][vpr][2 slots][3]
   const int C = c1 + c2;
   const int vpr = C / 8;
   const int cpg = C / groups;
   const int sample = blockIdx.y;
   const int r0 = blockIdx.x * chunk_rows;
   const int r1 = min(r0 + chunk_rows, rows_per_sample);
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int vec = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
   if (rsub < rows_par) {
     const int c0 = vec * 8;
     const bool first = c0 < c1;
     const int ld = first ? c1 : c2;
     const __half* src = (first ? x1 + c0 : x2 + (c0 - c1)) + (int64_t)sample * rows_per_sample * ld;
-    float s[8], q[8];
+    float s[8], q[8], piv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; piv[i] = 0.f; }
+    float cnt = 0.f;
+    int r = r0 + rsub;
+    if (r < r1) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        piv[2 * i] = f.x; piv[2 * i + 1] = f.y;
+      }
+    }
     auto add = [&](const uint4& v) {
       const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(h[i]);
-        s[2 * i] += f.x; q[2 * i] = fmaf(f.x, f.x, q[2 * i]);
-        s[2 * i + 1] += f.y; q[2 * i + 1] = fmaf(f.y, f.y, q[2 * i + 1]);
+        const float a = f.x - piv[2 * i], b = f.y - piv[2 * i + 1];
+        s[2 * i] += a; q[2 * i] = fmaf(a, a, q[2 * i]);
+        s[2 * i + 1] += b; q[2 * i + 1] = fmaf(b, b, q[2 * i + 1]);
       }
+      cnt += 1.f;
     };
-    int r = r0 + rsub;
     for (; r + 3 * rows_par < r1; r += 4 * rows_par) {
       const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld));
       const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(r + rows_par) * ld));
@@ -61,29 +91,85 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
       add(v0); add(v1); add(v2); add(v3);
     }
     for (; r < r1; r += rows_par) add(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld)));
-    // the 8 channels of a vector span at most two groups (cpg >= 8)
-    const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;
+    // the 8 channels of a vector span at most two groups (cpg >= 8): slot 0 = group c0 / cpg, slot 1 = the next one
+    const int g0 = c0 / cpg;
     const int split = (g0 + 1) * cpg - c0;
-    float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+    Moments ma{0.f, 0.f, 0.f}, mb{0.f, 0.f, 0.f};
+    if (cnt > 0.f) {
+      const float inv = 1.0f / cnt;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < split) { sa += s[i]; qa += q[i]; } else { sb += s[i]; qb += q[i]; }
+      for (int i = 0; i < 8; ++i) {
+        Moments m;
+        m.n = cnt;
+        m.mean = piv[i] + s[i] * inv;
+        m.m2 = fmaxf(q[i] - s[i] * s[i] * inv, 0.f);
+        if (i < split) ma = merge(ma, m); else mb = merge(mb, m);
+      }
     }
-    atomicAdd(&sm[2 * g0], sa);
-    atomicAdd(&sm[2 * g0 + 1], qa);
-    if (g1 != g0) {
-      atomicAdd(&sm[2 * g1], sb);
-      atomicAdd(&sm[2 * g1 + 1], qb);
-    }
+    float* o = sm + ((rsub * vpr + vec) * 2) * 3;
+    o[0] = ma.n; o[1] = ma.mean; o[2] = ma.m2;
+    o[3] = mb.n; o[4] = mb.mean; o[5] = mb.m2;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(int64_t)sample * 2 * groups + i], sm[i]);
+  // tree over the row lanes (fixed pairing)
+  for (int stride = 1; stride < rows_par; stride *= 2) {
+    if (rsub < rows_par && (rsub % (2 * stride)) == 0 && rsub + stride < rows_par) {
+      float* a = sm + ((rsub * vpr + vec) * 2) * 3;
+      const float* b = sm + (((rsub + stride) * vpr + vec) * 2) * 3;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const Moments m = merge(Moments{a[3 * sl], a[3 * sl + 1], a[3 * sl + 2]}, Moments{b[3 * sl], b[3 * sl + 1], b[3 * sl + 2]});
+        a[3 * sl] = m.n; a[3 * sl + 1] = m.mean; a[3 * sl + 2] = m.m2;
+      }
+    }
+    __syncthreads();
+  }
+  // group g: vectors [g*cpg/8, ((g+1)*cpg-1)/8], slot 0 where the vector starts inside g, slot 1 where it started in g-1
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const int v0 = (g * cpg) / 8, v1 = ((g + 1) * cpg - 1) / 8;
+    Moments acc{0.f, 0.f, 0.f};
+    for (int v = v0; v <= v1; ++v) {
+      const int gv = (v * 8) / cpg;                 // group of the vector's first channel
+      const float* e = sm + (v * 2 + (gv == g ? 0 : 1)) * 3;
+      acc = merge(acc, Moments{e[0], e[1], e[2]});
+    }
+    float* o = partials + (((int64_t)sample * gridDim.x + blockIdx.x) * groups + g) * 3;
+    o[0] = acc.n; o[1] = acc.mean; o[2] = acc.m2;
+  }
+}
+
+// one warp per (sample, group): fold the chunk partials -> (mean, rstd)
+__global__ void gn_finalize_kernel(const float* __restrict__ partials, int chunks, int groups, float eps, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int sample = blockIdx.y;
+  if (g >= groups) return;
+  Moments acc{0.f, 0.f, 0.f};
+  for (int c = lane; c < chunks; c += 32) {
+    const float* e = partials + (((int64_t)sample * chunks + c) * groups + g) * 3;
+    acc = merge(acc, Moments{e[0], e[1], e[2]});
+  }
+#pragma unroll
+  for (int off = 1; off < 32; off *= 2) {
+    Moments o;
+    o.n = __shfl_xor_sync(0xffffffffu, acc.n, off);
+    o.mean = __shfl_xor_sync(0xffffffffu, acc.mean, off);
+    o.m2 = __shfl_xor_sync(0xffffffffu, acc.m2, off);
+    // both partners must compute the same value: always merge (lower lane, higher lane)
+    acc = (lane & off) ? merge(o, acc) : merge(acc, o);
+  }
+  if (lane == 0) {
+    stats[((int64_t)sample * groups + g) * 2] = acc.mean;
+    stats[((int64_t)sample * groups + g) * 2 + 1] = rsqrtf(acc.m2 / acc.n + eps);
+  }
 }
 
 __global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, const float* __restrict__ gamma,
                 const float* __restrict__ beta, __half* __restrict__ y, int rows_per_sample, int groups, float eps, int silu,
                 int64_t perm_a, int64_t perm_b, int rows_par, int chunk_rows, const float* __restrict__ stats) {
+  (void)eps;
   const int C = c1 + c2;
   const int vpr = C / 8;
   const int cpg = C / groups;
@@ -100,14 +186,11 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   // y = x * scale + shift with scale = rstd * gamma, shift = beta - mean * rstd * gamma
   float scale[8], shift[8];
   {
-    const float inv_n = 1.0f / ((float)rows_per_sample * (float)cpg);
     const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;
     const int split = (g0 + 1) * cpg - c0;
-    const float2 sa = *reinterpret_cast<const float2*>(stats + ((int64_t)sample * groups + g0) * 2);
+    const float2 sa = *reinterpret_cast<const float2*>(stats + ((int64_t)sample * groups + g0) * 2);   // (mean, rstd)
     const float2 sb = *reinterpret_cast<const float2*>(stats + ((int64_t)sample * groups + g1) * 2);
-    const float mean0 = sa.x * inv_n, mean1 = sb.x * inv_n;
-    const float rstd0 = rsqrtf(fmaxf(sa.y * inv_n - mean0 * mean0, 0.f) + eps);
-    const float rstd1 = rsqrtf(fmaxf(sb.y * inv_n - mean1 * mean1, 0.f) + eps);
+    const float mean0 = sa.x, mean1 = sb.x, rstd0 = sa.y, rstd1 = sb.y;
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
     const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0)), bb = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
     const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
@@ -592,6 +675,25 @@ __global__ void ddim_cfg_step_kernel(float* __restrict__ lat, const float* __res
 
 using namespace a3d;
 
+static void gn_geometry(int C, int64_t samples, int64_t rows_per_sample, int* rows_par, int* threads, int* chunk_rows, int* chunks) {
+  const int vpr = C / 8;
+  int rp = 256 / vpr;
+  if (rp < 1) rp = 1;
+  *rows_par = rp;
+  *threads = ((rp * vpr + 31) / 32) * 32;   // <= 256 (C / 8 <= 160 for the UNet's widths) or one row per block
+  int cr = 128;
+  while (cr > 4 * rp && ((rows_per_sample + cr - 1) / cr) * samples < 592) cr /= 2;
+  *chunk_rows = cr;
+  *chunks = (int)((rows_per_sample + cr - 1) / cr);
+}
+
+extern "C" size_t a3d_group_norm_ws_bytes(int64_t samples, int64_t rows_per_sample, int c, int groups) {
+  if (c < 8 || samples < 1 || rows_per_sample < 1 || groups < 1) return 0;
+  int rows_par, threads, chunk_rows, chunks;
+  gn_geometry(c, samples, rows_per_sample, &rows_par, &threads, &chunk_rows, &chunks);
+  return sizeof(float) * ((size_t)2 * groups * samples + (size_t)3 * groups * samples * chunks);
+}
+
 extern "C" int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* y,
                               int64_t samples, int64_t rows_per_sample, int groups, float eps, int silu, int64_t perm_a,
                               int64_t perm_b, float* ws_stats, void* stream) {
@@ -601,22 +703,23 @@ extern "C" int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, co
   if (C % groups || C % 8 || c1 % 8 || c2 % 8 || C / 8 > 1024 || groups > 64)
     return fail(A3D_EINVAL, "a3d_group_norm: unsupported channels C=%d (c1=%d c2=%d) groups=%d", C, c1, c2, groups);
   if (rows_per_sample > (int64_t)1 << 30 || samples > 65535) return fail(A3D_EINVAL, "a3d_group_norm: extent too large");
-  A3D_CUDA_CHECK(cudaMemsetAsync(ws_stats, 0, sizeof(float) * 2 * groups * samples, st));
   const int vpr = C / 8;
-  int rows_par = 256 / vpr;
-  if (rows_par < 1) rows_par = 1;
-  const int threads = ((rows_par * vpr + 31) / 32) * 32;   // <= 256 (C / 8 <= 160 for the UNet's widths) or one row per block
+  int rows_par, threads, chunk_rows, chunks;
+  gn_geometry(C, samples, rows_per_sample, &rows_par, &threads, &chunk_rows, &chunks);
   if (threads > 512) return fail(A3D_EINVAL, "a3d_group_norm: C=%d too wide", C);
-  int chunk_rows = 128;
-  while (chunk_rows > 4 * rows_par && ((rows_per_sample + chunk_rows - 1) / chunk_rows) * samples < 592) chunk_rows /= 2;
-  dim3 grid((unsigned)((rows_per_sample + chunk_rows - 1) / chunk_rows), (unsigned)samples);
-  gn_stats_kernel<<<grid, threads, 2 * groups * sizeof(float), st>>>(reinterpret_cast<const __half*>(x1), c1,
-                                                                     reinterpret_cast<const __half*>(x2), c2,
-                                                                     (int)rows_per_sample, groups, rows_par, chunk_rows, ws_stats);
+  const size_t smem = (size_t)rows_par * vpr * 6 * sizeof(float);
+  if (smem > 48 * 1024) return fail(A3D_EINVAL, "a3d_group_norm: C=%d needs %zu B of shared memory", C, smem);
+  float* stats = ws_stats;                                          // [samples][groups][mean, rstd]
+  float* partials = ws_stats + 2 * (size_t)groups * samples;         // [samples][chunks][groups][n, mean, M2]
+  dim3 grid((unsigned)chunks, (unsigned)samples);
+  gn_stats_kernel<<<grid, threads, smem, st>>>(reinterpret_cast<const __half*>(x1), c1, reinterpret_cast<const __half*>(x2), c2,
+                                               (int)rows_per_sample, groups, rows_par, chunk_rows, partials);
+  A3D_LAUNCH_CHECK();
+  gn_finalize_kernel<<<dim3((groups + 7) / 8, (unsigned)samples), 256, 0, st>>>(partials, chunks, groups, eps, stats);
   A3D_LAUNCH_CHECK();
   gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __half*>(x1), c1, reinterpret_cast<const __half*>(x2), c2,
                                             gamma, beta, reinterpret_cast<__half*>(y), (int)rows_per_sample, groups, eps, silu,
-                                            perm_a, perm_b, rows_par, chunk_rows, ws_stats);
+                                            perm_a, perm_b, rows_par, chunk_rows, stats);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }

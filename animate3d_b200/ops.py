@@ -79,8 +79,15 @@ def temporal_attn(qkv: torch.Tensor, out: torch.Tensor, pixels: int, frames: int
                                   d, C.c_float(scale), L.stream_ptr()))
 
 
+def group_norm_ws_floats(samples: int, rows_per_sample: int, c: int, groups: int) -> int:
+    """fp32 elements of scratch a3d_group_norm needs for this geometry."""
+    lib = L.load()
+    return (int(lib.a3d_group_norm_ws_bytes(C.c_int64(samples), C.c_int64(rows_per_sample), c, groups)) + 3) // 4
+
+
 def group_norm(x1, c1, x2, c2, gamma, beta, y, samples, rows_per_sample, groups, eps, silu, ws_stats, perm=(0, 0)):
     lib = L.load()
+    assert ws_stats.numel() >= group_norm_ws_floats(samples, rows_per_sample, c1 + (c2 if x2 is not None else 0), groups)
     L.check(lib.a3d_group_norm(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(L.ptr(x2)), c2, C.c_void_p(gamma.data_ptr()),
                                C.c_void_p(beta.data_ptr()), C.c_void_p(y.data_ptr()), C.c_int64(samples),
                                C.c_int64(rows_per_sample), groups, C.c_float(eps), int(silu), C.c_int64(perm[0]),

@@ -313,6 +313,11 @@ class MVUNetMotionModel:
         for s in shape:
             numel *= s
         if t is None or t.numel() < numel or t.dtype != dtype:
+            if t is not None and self._graphs:
+                # graphs captured for other shape keys hold the old pointer: drop them, every key recaptures lazily
+                self._graphs.clear()
+                for st in self._static.values():
+                    st["calls"] = 0
             t = torch.empty(numel, dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t[:numel].view(*shape)
@@ -324,7 +329,8 @@ class MVUNetMotionModel:
 
     def _gn(self, x1, c1, x2, c2, gb, y, samples, rps, eps, silu, perm=(0, 0)):
         self.launches += 3
-        ws = self._buf("gn_stats", (samples * 64,), torch.float32)
+        ws = self._buf("gn_stats", (ops.group_norm_ws_floats(samples, rps, c1 + (c2 if x2 is not None else 0),
+                                                             self.cfg.norm_num_groups),), torch.float32)
         return ops.group_norm(x1, c1, x2, c2, gb[0], gb[1], y, samples, rps, self.cfg.norm_num_groups, eps, silu, ws, perm)
 
     def _ln(self, x, gb, y, rows, c):

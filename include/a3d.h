@@ -122,7 +122,12 @@ int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, in
 /* Replaces nn.GroupNorm (+ SiLU) of ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, TransformerTemporalModel.norm
  * (over frames) and conv_norm_out + conv_act (unet_motion_mv_model.py:262-266, 855-857).
  * GroupNorm over (rows_per_sample x C/groups) per sample, NHWC fp16.  x = concat(x1[C1], x2[C2]) along channels
- * (x2 may be NULL).  Optional SiLU.  Output rows may be permuted (perm_a, perm_b as in a3d_gemm). */
+ * (x2 may be NULL).  Optional SiLU.  Output rows may be permuted (perm_a, perm_b as in a3d_gemm).
+ * Statistics are reduced without atomics in a fixed order ((n, mean, M2) partials merged with Chan's formula: per-thread
+ * pivoted sums -> shared-memory tree -> warp-shuffle tree), so results are bit-reproducible and free of the
+ * E[x^2]-E[x]^2 cancellation.  ws_stats: caller-owned scratch of a3d_group_norm_ws_bytes(samples, rows_per_sample, c1+c2,
+ * groups) bytes (no initialisation needed). */
+size_t a3d_group_norm_ws_bytes(int64_t samples, int64_t rows_per_sample, int c, int groups);
 int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* y,
                    int64_t samples, int64_t rows_per_sample, int groups, float eps, int silu, int64_t perm_a,
                    int64_t perm_b, float* ws_stats, void* stream);
@@ -256,8 +261,9 @@ int a3d_knn_graph(const float* points, int n, int K, int32_t* nbr, float* dist2,
 int a3d_arap(const float* nodes, int Nt, int Nv, const int32_t* nbr, int K, const float* weight, const int32_t* sample, int Ns,
              float* err, float* grad, void* stream);
 
-/* debug hook: per-step clock64 timestamps of CTA (0,0,0) of the following head-dim-40 attention launches (NULL = off) */
-int a3d_debug_set_attn_trace(void* device_buffer_1024_int64);
+/* debug hook: a device uint64 counter the tcgen05 attention kernels bump once per (warp, key step) that takes the
+   lazy-rescale branch of the single-pass softmax (NULL = off; tests use it to prove adversarial inputs reach that branch) */
+int a3d_debug_set_attn_trace(void* device_counter_u64);
 /* same for the tcgen05 GEMM: per-tile timestamps of CTA 0 (epilogue warp 0 and the MMA-issuing thread) */
 int a3d_debug_set_gemm_trace(void* device_buffer_1024_int64);
 

@@ -300,8 +300,17 @@ def batch_to_head(x: Tensor, heads: int) -> Tensor:
 
 def mea(q: Tensor, k: Tensor, v: Tensor, scale: float) -> Tensor:
     """xformers.ops.memory_efficient_attention(q,k,v,attn_bias=None,scale) on [B*heads, L, d] inputs."""
-    s = torch.bmm(q, k.transpose(1, 2)) * scale
-    return torch.bmm(torch.softmax(s, dim=-1), v)
+    # batches are independent: evaluate them in chunks so the [chunk, L, L] score tensor stays below ~1 GiB (same result;
+    # the headline 4-view x 16-frame config would otherwise materialise 2 x 8.6 GB per cross-view attention)
+    step = max(1, (1 << 28) // max(1, q.shape[1] * k.shape[1]))
+    if step >= q.shape[0]:
+        s = torch.bmm(q, k.transpose(1, 2)) * scale
+        return torch.bmm(torch.softmax(s, dim=-1), v)
+    out = torch.empty(q.shape[0], q.shape[1], v.shape[2], dtype=q.dtype)
+    for i in range(0, q.shape[0], step):
+        s = torch.bmm(q[i:i + step], k[i:i + step].transpose(1, 2)) * scale
+        out[i:i + step] = torch.bmm(torch.softmax(s, dim=-1), v[i:i + step])
+    return out
 
 
 def feed_forward(sd, p, x):

@@ -292,9 +292,12 @@ def test_group_norm(case, silu):
     gamma = torch.randn(C, device=DEV, generator=g)
     beta = torch.randn(C, device=DEV, generator=g)
     y = torch.empty(samples * rps, C, device=DEV, dtype=torch.float16)
-    ws = torch.empty(samples * 64, device=DEV)
+    ws = torch.empty(ops.group_norm_ws_floats(samples, rps, C, 32), device=DEV)
     perm = (rps // 4, 4) if c2 == 0 else (0, 0)
     ops.group_norm(x1, c1, x2, c2, gamma, beta, y, samples, rps, 32, 1e-5, silu, ws, perm=perm)
+    y2 = torch.empty_like(y)
+    ops.group_norm(x1, c1, x2, c2, gamma, beta, y2, samples, rps, 32, 1e-5, silu, ws, perm=perm)
+    assert torch.equal(y, y2), "GroupNorm statistics are reduced in a fixed order: repeated calls must be bit-identical"
     x = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], 1)
     xr = x.reshape(samples, rps, C).permute(0, 2, 1)
     ref = F.group_norm(xr, 32, gamma, beta, 1e-5)
@@ -306,6 +309,25 @@ def test_group_norm(case, silu):
     out[perm_rows(rows, *perm)] = ref
     torch.cuda.synchronize()
     close(y, out, what=f"group_norm {case}")
+
+
+@pytest.mark.parametrize("case", [(2, 16 * 1024, 320), (8, 16 * 256, 640), (3, 100, 1280), (2, 7, 2560)], ids=lambda c: "s%d_r%d_c%d" % c)
+def test_group_norm_large_mean_small_variance(case):
+    """|mean| >> std (here 200 : 0.05): the E[x^2]-E[x]^2 form loses every significant digit of the variance in fp32; the
+    pivoted (n, mean, M2) merge does not.  Also covers the over-frames geometry of the motion modules (16 x 1024 rows)."""
+    ops, _ = _ops()
+    samples, rps, c = case
+    g = torch.Generator(device=DEV).manual_seed(sum(case))
+    x = (200.0 + 0.0625 * torch.randn(samples * rps, c, device=DEV, generator=g)).half()    # fp16 spacing at 200 is 0.125
+    gamma = torch.randn(c, device=DEV, generator=g)
+    beta = torch.randn(c, device=DEV, generator=g)
+    y = torch.empty_like(x)
+    ws = torch.empty(ops.group_norm_ws_floats(samples, rps, c, 32), device=DEV)
+    ops.group_norm(x, c, None, 0, gamma, beta, y, samples, rps, 32, 1e-5, 0, ws)
+    xr = x.double().reshape(samples, rps, c).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, gamma.double(), beta.double(), 1e-5).permute(0, 2, 1).reshape(samples * rps, c)
+    torch.cuda.synchronize()
+    close(y, ref.float(), what=f"group_norm large mean {case}")
 
 
 @pytest.mark.parametrize("c", [320, 640, 1280])
