@@ -18,7 +18,7 @@
 
 namespace a3d {
 
-constexpr int kArapMaxK = 8;
+constexpr int kArapMaxK = 12;   // the reference's default K is 10 (systems/util.py:58, 183); shipped configs use 3
 
 // eigenvector (w, x, y, z) of the largest eigenvalue of the symmetric 4x4 matrix a (destroyed)
 A3D_HD void sym4_max_eigvec(float (&a)[4][4], float (&q)[4]) {

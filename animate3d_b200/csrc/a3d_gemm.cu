@@ -563,7 +563,7 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   d.a_mode = a->a_mode;
   d.bias = a->bias; d.rowbias = a->rowbias; d.rb_ld = a->rb_ld;
   d.rb_div = a->rb_div > 0 ? a->rb_div : 1; d.rb_mod = a->rb_mod > 0 ? a->rb_mod : (int64_t)1 << 40;
-  d.acc_scale = a->acc_scale == 0.f ? 1.f : a->acc_scale;
+  d.acc_scale = a->acc_scale;   // the caller passes 1.0 when unused; 0 is a legitimate blend weight, not a sentinel
   d.R1 = reinterpret_cast<const __half*>(a->R1); d.ldr1 = a->ldr1; d.r1_scale = a->r1_scale;
   d.R2 = reinterpret_cast<const __half*>(a->R2); d.ldr2 = a->ldr2;
   d.C = a->C; d.ldc = a->ldc; d.geglu = a->geglu; d.out_f32 = a->out_f32;

@@ -317,7 +317,8 @@ __global__ void layer_norm_generic_kernel(const __half* __restrict__ x, const fl
 // one block per pixel; thread = (head, query frame).  K/V rows of the pixel are staged in shared memory (all queries of
 // a head read the same K/V address -> broadcast); the thread's query row lives in registers.
 template <int D>
-__global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int frames, int heads, float scale) {
+__global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int frames, int heads, float scale,
+                                     int64_t ldo) {
   extern __shared__ __align__(16) uint8_t smraw[];
   __half* s = reinterpret_cast<__half*>(smraw);          // [frames][2*C]: k | v
   const int C = heads * D;
@@ -360,7 +361,7 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
   float sum = 0.f;
   for (int j = 0; j < frames; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
   const float inv = 1.0f / sum;
-  __half* o = out + (pix * frames + f) * C + h * D;
+  __half* o = out + (pix * frames + f) * ldo + h * D;
 #pragma unroll
   for (int c = 0; c < D / 8; ++c) {
     float acc[8];
@@ -395,7 +396,7 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
 // the wide levels keep ~7 blocks per SM instead of one 123 KB block.
 template <int D, int HB>
 __global__ void __launch_bounds__(HB * 32) temporal_attn16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int heads,
-                                                                 float scale_log2) {
+                                                                 float scale_log2, int64_t ldo) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int C = heads * D;
   constexpr int CB = HB * D;                   // channels of this block's heads
@@ -480,10 +481,10 @@ __global__ void __launch_bounds__(HB * 32) temporal_attn16_kernel(const __half* 
     }
   }
   __syncthreads();
-  __half* obase = out + pix * 16 * C + hb0 * D;
+  __half* obase = out + pix * 16 * ldo + hb0 * D;
   for (int i = threadIdx.x; i < 16 * vseg; i += blockDim.x) {
     const int f = i / vseg, vv = i % vseg;
-    *reinterpret_cast<uint4*>(obase + (int64_t)f * C + vv * 8) = *reinterpret_cast<const uint4*>(sm + f * ld + vv * 8);
+    *reinterpret_cast<uint4*>(obase + (int64_t)f * ldo + vv * 8) = *reinterpret_cast<const uint4*>(sm + f * ld + vv * 8);
   }
 }
 
@@ -745,12 +746,13 @@ extern "C" int a3d_layer_norm(const void* x, const float* gamma, const float* be
 }
 
 template <int D>
-static int launch_temporal(const void* qkv, void* out, int64_t pixels, int frames, int heads, float scale, cudaStream_t st) {
+static int launch_temporal(const void* qkv, void* out, int64_t pixels, int frames, int heads, float scale, int64_t ldo,
+                           cudaStream_t st) {
   constexpr int HB = 320 / D;   // 8 / 4 / 2 heads per block
   if (frames == 16 && heads % HB == 0 && heads / HB <= 65535) {
     const size_t smem16 = (size_t)16 * (3 * HB * D + 8) * 2;   // 31 KB
     temporal_attn16_kernel<D, HB><<<dim3((unsigned)pixels, (unsigned)(heads / HB)), HB * 32, smem16, st>>>(
-        reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), heads, scale * 1.4426950408889634f);
+        reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), heads, scale * 1.4426950408889634f, ldo);
     A3D_LAUNCH_CHECK();
     return A3D_OK;
   }
@@ -762,19 +764,22 @@ static int launch_temporal(const void* qkv, void* out, int64_t pixels, int frame
   }
   const int threads = ((frames * heads + 31) / 32) * 32;
   temporal_attn_kernel<D><<<(unsigned)pixels, threads, smem, st>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out),
-                                                                   frames, heads, scale);
+                                                                   frames, heads, scale, ldo);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
 
 extern "C" int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, int heads, int d, float scale,
-                                 void* stream) {
+                                 int64_t ldo, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (frames > 32 || frames * heads > 1024) return fail(A3D_EINVAL, "a3d_temporal_attn: frames=%d heads=%d", frames, heads);
+  if (ldo == 0) ldo = (int64_t)heads * d;
+  if (ldo < (int64_t)heads * d || ldo % 8 || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(A3D_EINVAL, "a3d_temporal_attn: output row stride %lld must be >= C, a multiple of 8, 16-byte aligned base", (long long)ldo);
   switch (d) {
-    case 40: return launch_temporal<40>(qkv, out, pixels, frames, heads, scale, st);
-    case 80: return launch_temporal<80>(qkv, out, pixels, frames, heads, scale, st);
-    case 160: return launch_temporal<160>(qkv, out, pixels, frames, heads, scale, st);
+    case 40: return launch_temporal<40>(qkv, out, pixels, frames, heads, scale, ldo, st);
+    case 80: return launch_temporal<80>(qkv, out, pixels, frames, heads, scale, ldo, st);
+    case 160: return launch_temporal<160>(qkv, out, pixels, frames, heads, scale, ldo, st);
     default: return fail(A3D_EINVAL, "a3d_temporal_attn: head dim %d not in {40,80,160}", d);
   }
 }

@@ -73,10 +73,12 @@ def attention(q: L.View5, k: L.View5, v: L.View5, out: torch.Tensor, ostrides, *
     L.check(lib.a3d_attention(C.byref(a), L.stream_ptr()))
 
 
-def temporal_attn(qkv: torch.Tensor, out: torch.Tensor, pixels: int, frames: int, heads: int, d: int, scale: float):
+def temporal_attn(qkv: torch.Tensor, out: torch.Tensor, pixels: int, frames: int, heads: int, d: int, scale: float,
+                  ldo: int = 0, out_col_offset: int = 0):
+    """out rows have stride `ldo` halves (0 = heads*d) and start at column `out_col_offset` of `out`."""
     lib = L.load()
-    L.check(lib.a3d_temporal_attn(C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int64(pixels), frames, heads,
-                                  d, C.c_float(scale), L.stream_ptr()))
+    L.check(lib.a3d_temporal_attn(C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr() + 2 * out_col_offset), C.c_int64(pixels),
+                                  frames, heads, d, C.c_float(scale), C.c_int64(ldo), L.stream_ptr()))
 
 
 def group_norm_ws_floats(samples: int, rows_per_sample: int, c: int, groups: int) -> int:

@@ -213,8 +213,11 @@ class MVUNetMotionModel:
             wv = _pad_heads(sd[f"{a1}.to_v.weight"], heads, d, dv)
             wqkv = torch.cat([wq, wqi, wk, wv], 0)
             t["qkv"] = _Lin(wqkv, _ones_bias(heads, d, dv, 3 * heads * dqk, wqkv.shape[0], "cpu"), dev)
-            t["out_i2v"] = lin(f"{a1}.processor.to_out_i2v")
-            t["out1"] = lin(f"{a1}.to_out.0")
+            # to_out(O1 + to_out_i2v(O2)) (attention_processor.py:423-431) is ONE GEMM over [O1 | O2] with K = 2C:
+            #   [O1 | O2] [W_out | W_out W_i2v]^T + (b_out + W_out b_i2v)   -- products formed in fp32, rounded to fp16 once
+            w_out, b_out = sd[f"{a1}.to_out.0.weight"].float(), sd[f"{a1}.to_out.0.bias"].float()
+            w_i2v, b_i2v = sd[f"{a1}.processor.to_out_i2v.weight"].float(), sd[f"{a1}.processor.to_out_i2v.bias"].float()
+            t["out1"] = _Lin(torch.cat([w_out, w_out @ w_i2v], 1), b_out + w_out @ b_i2v, dev)
             a2 = f"{tb}.attn2"
             t["q2"] = _Lin(_pad_heads(sd[f"{a2}.to_q.weight"], heads, d, dqk), None, dev)
             t["out2"] = lin(f"{a2}.to_out.0")
@@ -246,12 +249,16 @@ class MVUNetMotionModel:
                 wsp = torch.cat([_pad_heads(sd[f"{pp}.to_q_sp.weight"], heads, d, dqk),
                                  _pad_heads(sd[f"{pp}.to_k_sp.weight"], heads, d, dqk),
                                  _pad_heads(sd[f"{pp}.to_v_sp.weight"], heads, d, dv)], 0)
-                alpha = torch.sigmoid(sd[f"{pp}.alpha_blender.mix_factor"]).item()
+                # AlphaBlender (attention_processor.py:700-713): alpha * to_out_sp(S) + (1 - alpha) * to_out(T) is ONE GEMM over
+                # [S | T] with K = 2C: weights [alpha W_sp | (1 - alpha) W_t], bias alpha b_sp + (1 - alpha) b_t (alpha is a
+                # tensor all the way: a mix_factor whose sigmoid underflows to exactly 0 or 1 stays exact)
+                alpha = torch.sigmoid(sd[f"{pp}.alpha_blender.mix_factor"].float()).reshape(())
+                w_sp, b_sp = sd[f"{pp}.to_out_sp.weight"].float(), sd[f"{pp}.to_out_sp.bias"].float()
+                w_t, b_t = sd[f"{ap}.to_out.0.weight"].float(), sd[f"{ap}.to_out.0.bias"].float()
                 m[a] = {"t_qkv": _Lin(wt, None, dev), "t_table": (pe @ wt.t()).to(dev).contiguous(),          # [32, 3c]
-                        "t_out": lin(f"{ap}.to_out.0"),
                         "s_qkv": _Lin(wsp, _ones_bias(heads, d, dv, 2 * heads * dqk, wsp.shape[0], "cpu"), dev),
                         "s_table": (pos2d @ wsp.t()).to(dev).contiguous(),                                      # [hw, Nsp]
-                        "s_out": lin(f"{pp}.to_out_sp"), "alpha": alpha}
+                        "out": _Lin(torch.cat([alpha * w_sp, (1 - alpha) * w_t], 1), alpha * b_sp + (1 - alpha) * b_t, dev)}
             m["ff1"] = _Lin(_geglu_interleave(sd[f"{tb}.ff.net.0.proj.weight"]), _geglu_interleave(sd[f"{tb}.ff.net.0.proj.bias"]), dev)
             m["ff2"] = lin(f"{tb}.ff.net.2")
             return m
@@ -425,19 +432,18 @@ class MVUNetMotionModel:
             # views span ranks: local rows are (b f p) of ONE view; K|V of every view are all-gathered
             vq, vqi, vk, vv = self._gathered_views(ln, t["qkv"], 2 * hq, M, lvl, hq, (lambda n_: (n_, F * hw * n_, hw * n_, F * hw * n_)),
                                                    (lambda n_: (n_, M * n_, hw * n_, F * hw * n_)), hw, F, B, None, 0, 0)
-        o1 = self._buf(f"ao{lvl}", (M, c))
-        o2 = self._buf(f"ao2_{lvl}", (M, c))
-        self._attn(vq, vk, vv, o1, ostr, d)
-        self._attn(vqi, vk, vv, o2, ostr, d, kv_i3_zero=True)
-        tmp = self._buf(f"tmp{lvl}", (M, c))
-        self._gemm(o2, t["out_i2v"], tmp, M, R1=o1, ldr1=c, r1_scale=1.0)       # O1 + to_out_i2v(O2)
-        self._gemm(tmp, t["out1"], tok, M, R2=tok, ldr2=c)                       # to_out(.) + residual
+        o12 = self._buf(f"ao{lvl}", (M, 2 * c))                                  # [O1 | O2], rows of 2C
+        ostr12 = tuple(2 * s_ for s_ in ostr)
+        self._attn(vq, vk, vv, o12, ostr12, d)
+        self._attn(vqi, vk, vv, o12, ostr12, d, kv_i3_zero=True, out_col_offset=c)
+        self._gemm(o12, t["out1"], tok, M, R2=tok, ldr2=c)                       # to_out(O1 + to_out_i2v(O2)) + residual
         # ---- attn2: text (77) + image (4) cross attention, K/V shared by the F frames of a view
         self._ln(tok, t["ln2"], ln, M, c)
         q2 = qkv.view(-1)[: M * hq].view(M, hq)
         self._gemm(ln, t["q2"], q2, M)
         vq2 = ops.view5(q2, 0, hq, (hq, hw * hq, hw * hq, F * hw * hq), (hw, 1, F, B * Nv))
         ostr2 = (c, hw * c, hw * c, F * hw * c)
+        o1 = o12.view(-1)[: M * c].view(M, c)
         for kvbuf, lk, accumulate, sc in ((self._kv_text, self._n_text, False, 1.0), (self._kv_ip, cfg.ip_num_tokens, True, cfg.ip_scale)):
             ld = kvbuf.shape[1]
             off = t["kv_off"]
@@ -466,9 +472,7 @@ class MVUNetMotionModel:
         self._gemm(g, m["proj_in"], tok, M)
         ln = self._buf(f"ln{lvl}", (M, c))
         tq = self._buf(f"tqkv{lvl}", (M, 3 * c))
-        ao = self._buf(f"ao{lvl}", (M, c))
-        ao2 = self._buf(f"ao2_{lvl}", (M, c))
-        tmp = self._buf(f"tmp{lvl}", (M, c))
+        st2 = self._buf(f"ao{lvl}", (M, 2 * c))                                  # [S | T]: cross-view branch | temporal branch
         hq = heads * dqk
         for a, lnk in (("attn1", "ln1"), ("attn2", "ln2")):
             p = m[a]
@@ -476,8 +480,7 @@ class MVUNetMotionModel:
             # temporal branch: (x + pe_t) W == x W + table[f]
             self._gemm(ln, p["t_qkv"], tq, M, rowbias=p["t_table"], rb_div=1, rb_mod=F)
             self.launches += 1
-            ops.temporal_attn(tq, ao, M // F, F, heads, d, d ** -0.5)
-            self._gemm(ao, p["t_out"], tmp, M)
+            ops.temporal_attn(tq, st2, M // F, F, heads, d, d ** -0.5, ldo=2 * c, out_col_offset=c)
             # spatial (cross-view) branch: (x + pos2d) W == x W + table[p]
             ns = p["s_qkv"].n
             if self.view_group is None:
@@ -491,10 +494,9 @@ class MVUNetMotionModel:
             else:
                 vq, _, vk, vv = self._gathered_views(ln, p["s_qkv"], hq, M, lvl, hq, (lambda n_: (F * n_, hw * F * n_, n_, hw * F * n_)),
                                                      (lambda n_: (F * n_, M * n_, n_, hw * F * n_)), hw, F, B, p["s_table"], F, hw)
-            self._attn(vq, vk, vv, ao2, (F * c, hw * F * c, c, Nv * hw * F * c), d)
-            # AlphaBlender: alpha * (to_out_sp(S)) + (1 - alpha) * T, plus the block residual, in one epilogue
-            al = p["alpha"]
-            self._gemm(ao2, p["s_out"], tok, M, acc_scale=al, R1=tmp, ldr1=c, r1_scale=1.0 - al, R2=tok, ldr2=c)
+            self._attn(vq, vk, vv, st2, (2 * F * c, 2 * hw * F * c, 2 * c, 2 * Nv * hw * F * c), d)
+            # AlphaBlender of both branches' output projections + the block residual: one GEMM, K = 2C
+            self._gemm(st2, p["out"], tok, M, R2=tok, ldr2=c)
         self._ff(tok, m["ln3"], m["ff1"], m["ff2"], M, c, lvl)
         # proj_out, rows back to (bn f p), + residual
         self._gemm(tok, m["proj_out"], x, M, perm=(hw, F), R2=x, ldr2=c)

@@ -62,7 +62,7 @@ typedef struct a3d_gemm_args {
   const float* bias;          /* [N] or NULL */
   const float* rowbias;       /* [rb_rows, rb_ld] or NULL */
   int64_t rb_ld, rb_div, rb_mod;
-  float acc_scale;            /* 1.0 if unused */
+  float acc_scale;            /* multiplies the accumulator: MUST be set (1.0 if unused; 0.0 is honoured, not remapped) */
   const void* R1; int64_t ldr1; float r1_scale;   /* fp16 or NULL */
   const void* R2; int64_t ldr2;                   /* fp16 or NULL */
   int geglu;
@@ -116,7 +116,9 @@ int a3d_attention(const a3d_attn_args* args, void* stream);
 /* Temporal attention over F frames for every (pixel, head): qkv [P, F, 3*C] fp16 (q | k | v), out [P, F, C].
  * Replaces the attention of the motion modules' temporal transformer blocks (diffusers TransformerTemporalModel reached
  * from unet_motion_mv_model.py:790-836) and the temporal branch of attention_processor.py:541-723 (line 103's call). */
-int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, int heads, int d, float scale, void* stream);
+int a3d_temporal_attn(const void* qkv, void* out, int64_t pixels, int frames, int heads, int d, float scale, int64_t ldo,
+                      void* stream);   /* ldo: output row stride in halves (0 = C): lets the result land in a column block of a
+                                          wider buffer, e.g. next to the cross-view branch for the merged output projection */
 
 /* ---------------------------------------------------------------- normalisation / elementwise ---------------- */
 /* Replaces nn.GroupNorm (+ SiLU) of ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, TransformerTemporalModel.norm

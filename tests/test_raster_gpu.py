@@ -168,3 +168,54 @@ def test_reference_style_api_and_sh_colour():
     assert m2.grad is not None and m2.grad.abs().sum() > 0 and shc.grad.abs().sum() > 0
     with pytest.raises(Exception):
         GaussianRasterizer(settings[0])(xyz.cuda(), m2, o.cuda(), scales=s.cuda(), rotations=q.cuda())
+
+
+def test_config3_size_indices_bit_exact_and_overflow_retry():
+    """BASELINE config 3 geometry: 50 000 gaussians at 512x512 (1024 tiles per camera), 8 cameras in one batch.  Sorted
+    keys / point_list / ranges / radii bit-exact for EVERY camera (the global sort key is (camera*1024+tile) << 32 | depth:
+    45 significant bits), images checked on one camera.  The first attempt runs with a deliberately tiny pair capacity, so
+    the overflow -> grow -> redo path of `_RasterizeBatch.forward` (rasterizer.py) is the one that produces the result."""
+    from animate3d_b200 import rasterizer as RZ
+    from oracle import raster_oracle as R
+    P, H, W, ncam, seed = 50000, 512, 512, 8, 11
+    xyz, s, q, o, sh = _scene(P, seed, scale_mul=1.0)          # config-3 scales (SURVEY 8d), not the enlarged test scenes
+    bg = torch.tensor([0.5, 0.5, 0.5])
+    cams = R.random_cameras(4, seed) + R.random_cameras(4, seed + 1)
+    settings, raw = _settings(cams, H, W, bg)
+    col = torch.clamp(R.SH_C0 * sh[:, 0] + 0.5, min=0)
+    cams_t = RZ._pack_cams(settings, "cuda")
+    meta = (H, W, 0, False, 1.0, bg.tolist())
+
+    class Ctx:
+        def save_for_backward(self, *a): self.saved = a
+        def mark_non_differentiable(self, *a): pass
+
+    def forward():
+        ctx = Ctx()
+        out = RZ._RasterizeBatch.forward(ctx, xyz.cuda(), None, s.cuda(), q.cuda(), o.cuda(), None, col.cuda(), cams_t, meta)
+        return ctx, out
+
+    key = (P, H, W, ncam)
+    RZ._cap_hint[key] = 1 << 12                                 # far below the ~1e6 pairs of this scene: must overflow
+    ctx, (color, radii, depth, alpha) = forward()
+    total = int(ctx.num_rendered.sum())
+    assert total > (1 << 12), "scene too small to overflow the forced capacity"
+    assert ctx.meta[1] >= total, "retry must have grown the capacity to hold every pair"
+    ctx2, (color2, radii2, depth2, alpha2) = forward()          # second call: capacity hint from the first, no retry
+    assert torch.equal(color, color2) and torch.equal(depth, depth2) and torch.equal(alpha, alpha2) and torch.equal(radii, radii2)
+    tables = _binning_tables(P, H, W, ncam, ctx.num_rendered, ctx.saved[-1], ctx.meta[1])
+    for c, (wv, full, cp, tf) in enumerate(raw):
+        pre = R.preprocess(xyz, s, q, o, None, col, 0, wv, full, cp, tf, tf, H, W, 1.0)
+        keys, pl, ranges = R.binning(pre, H, W)
+        assert int(ctx.num_rendered[c]) == len(keys), f"cam {c}: pair count {int(ctx.num_rendered[c])} != {len(keys)}"
+        assert torch.equal(radii[c].cpu(), pre.radii), f"cam {c}: radii"
+        k, p_, rg = tables[c]
+        assert np.array_equal(k, keys), f"cam {c}: sorted keys differ"
+        assert np.array_equal(p_, pl), f"cam {c}: point_list differs"
+        assert np.array_equal(rg, ranges), f"cam {c}: tile ranges differ"
+        if c == ncam - 1:                                       # the LAST camera: highest tile ids of the global key space
+            col_o, dep_o, alp_o, _, _ = R.render(pre, pl, ranges, H, W, bg)
+            for name, got, ref in (("color", color[c].cpu(), col_o), ("depth", depth[c].cpu(), dep_o), ("alpha", alpha[c].cpu(), alp_o)):
+                bad = ((got - ref).abs() > 3e-5 + 1e-4 * ref.abs())
+                assert bad.sum().item() <= 16, f"cam {c} {name}: {bad.sum().item()} pixels off"
+                assert (got - ref).abs().max().item() < 5e-3, f"cam {c} {name}"

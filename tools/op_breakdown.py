@@ -41,7 +41,7 @@ def attn_sig(q, k, v, out, ostrides, *, heads, d, **kw):
 
 wrap("gemm", gemm_sig)
 wrap("attention", attn_sig)
-wrap("temporal_attn", lambda qkv, out, pixels, frames, heads, d, scale: (f"pixels={pixels} F={frames} d={d}", 4.0 * pixels * heads * frames * frames * d))
+wrap("temporal_attn", lambda qkv, out, pixels, frames, heads, d, scale, **kw: (f"pixels={pixels} F={frames} d={d}", 4.0 * pixels * heads * frames * frames * d))
 wrap("group_norm", lambda x1, c1, x2, c2, *a, **k: (f"c={c1 + c2} samples={a[3]} rows={a[4]}", 0.0))
 wrap("layer_norm", lambda x, g, b, y, rows, c, eps=1e-5: (f"rows={rows} c={c}", 0.0))
 wrap("conv_in", lambda sample, w, b, y, bn, cin, f, h, wd, cout: (f"{cin}->{cout} pixels={bn * f * h * wd}", 2.0 * bn * f * h * wd * cout * cin * 9))
