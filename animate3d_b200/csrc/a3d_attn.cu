@@ -658,6 +658,59 @@ attn4_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// softmax arithmetic of the v5 kernel
+//   * the exponent offset carries a fixed bias: P' = 2^(y + kPBias) with y = s*scale*log2e - stabiliser.  The bias cancels in
+//     O / rowsum (the row sum is the ones column of V, accumulated from the same P'); it moves the fp16 flush-to-zero point from
+//     2^-14 to 2^-24 of the stabiliser, so the polynomial path below and the MUFU+F2FP path drop the same (negligible) tail.
+//     Head-room: y <= kRescale5 (stale stabiliser), so P' <= 2^(4+10) < 65504.
+//   * MUFU path  : ex2.approx(y + bias) per score, cvt.rn.f16x2 per pair            -> 20 XU-pipe cycles per pair
+//   * poly path  : 2^y on the FMA pipe in half2 arithmetic, Cody-Waite style:        ->  4 XU-pipe cycles per pair (the cvt)
+//       h = cvt.f16x2(y); h = max(h, -25); t = h + 1536 (rounds to integer: fp16 ulp is 1 there); n = t - 1536; f = h - n in
+//       [-0.5, 0.5]; p = c0 + f(c1 + f(c2 + f c3)) (minimax for 2^f, 6.9e-4 max / 2.5e-4 rms relative in fp16);
+//       2^(n + bias) is built as fp16 bits ((n + 25) << 10) from the low 6 mantissa bits of t and multiplied in (exact).
+//     Precision of y in fp16 matters only near the stabiliser (|y| < 4: ulp <= 2^-9 -> 7e-4 relative in 2^y); far below it the
+//     weights are small.  MUFU.EX2 is 8 cycles per warp instruction and shares its pipe with F2FP (profiles/
+//     r01_pipes_ubench.txt): moving POLY of every 4 pairs off it lowers the pipe floor from 20 to 20 - 4*POLY cycles per pair.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float kPBias = 10.0f;
+constexpr float kRescale5 = 4.0f;
+
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t exp2_h2(uint32_t h) {   // h: two fp16 exponents <= ~5; returns fp16x2 2^(h + kPBias)
+  uint32_t t, n, f, pl, e, r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(h) : "r"(h), "r"(0xCE40CE40u));            // -25.0: everything below flushes to 0
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(t) : "r"(h), "r"(0x66006600u));          // + 1536.0
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(n) : "r"(t), "r"(0x66006600u));
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(f) : "r"(h), "r"(n));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(pl) : "r"(0x2B112B11u), "r"(f), "r"(0x33C433C4u));   // c3 f + c2
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(pl) : "r"(pl), "r"(f), "r"(0x398C398Cu));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(pl) : "r"(pl), "r"(f), "r"(0x3C003C00u));
+  // exponent field (n + 25 + ... ) : t = 0x6600 + n per half -> low 6 bits = n mod 64; + 25 -> 0 .. 29 for n in [-25, 4]
+  asm("mad.lo.u32 %0, %1, 1024, %2;" : "=r"(e) : "r"(t), "r"(0x64006400u));
+  e &= 0x7C007C00u;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(pl), "r"(e));
+  return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // v5 (head_dim 40): v4 with the two key halves of a step made INDEPENDENT.  In v4 the two warps that share a 32-row
 //   quadrant keep one stabiliser and meet at a named barrier every step; both sit on the same SM sub-partition, so they
 //   behave like one 64-key warp and the MUFU pipe still idles ~37% of the time (profiles/r01_ncu_attn4.txt).  Here each half
@@ -871,6 +924,11 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       uint64_t* my_pv_done = pv_done + (2 * g + h) * 2;
       const int rows_tile = p.k_box1 * p.k_box2;   // keys a full tile holds (<= 64)
       // 16-column chunks of O this half rescales / writes out
+      const uint32_t sP_u32 = smem_u32(sP);
+      uint32_t p_off[4];      // this thread's four 16-byte P chunks of a step (128B-swizzled row r, chunks 4h .. 4h+3)
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) p_off[c16] = sw128_offset(r, 4 * h + c16);
+      const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2);
       const int oc0 = h ? Cfg::kOChunks0 : 0, oc1 = h ? Cfg::kOChunks : Cfg::kOChunks0;
       for (int j = 0; j < n; ++j) {
         const int valid = ((j == n - 1) ? p.rows_k : rows_tile) - 32 * h;   // valid keys among this half's 32 columns
@@ -897,15 +955,15 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           }
           m_run = fmaxf(fmaxf(mx0, mx1) * p.scale_log2, -1.0e30f);
         }
-        uint8_t* sPg = sP + b * Cfg::kPBox;
+        const uint32_t sPg = sP_u32 + b * Cfg::kPBox;
         if (j >= 2) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);   // P columns of step j-2 consumed (long ago)
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
           // Single pass with a STALE stabiliser (the running max of the previous steps); this step's max is accumulated in
-          // the same loop.  Only when a row's new max exceeds the stabiliser by more than kRescaleLog2 (P could overflow
+          // the same loop.  Only when a row's new max exceeds the stabiliser by more than kRescale5 (P could overflow
           // fp16) is the step redone with the updated stabiliser -- after the first few steps that never happens.
           float mx0 = -INFINITY, mx1 = -INFINITY;
-          const float neg_m = POLY == 3 ? -(m_run + kPackBias) : -m_run;
+          const uint64_t nm_mufu = pack2(kPBias - m_run, kPBias - m_run), nm_poly = pack2(-m_run, -m_run);
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
             uint4 q;
@@ -915,23 +973,17 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
               const int i = c16 * 8 + 2 * t;
               const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]);
               if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
-              const bool poly = POLY == 1 ? (t == 1) : POLY == 2 ? (t & 1) : false;
-              const float y0 = fmaf(s0, p.scale_log2, neg_m), y1 = fmaf(s1, p.scale_log2, neg_m);
-              if (POLY == 3) {
-                // F2FP shares the MUFU pipe (4 of the 20 pipe cycles of a pair): pack on the ALU pipe instead.  neg_m carries
-                // an extra -112, so the fp32 bits of 2^(y-112) shifted right by 13 ARE the fp16 bits of 2^y (truncated; the
-                // bias of the truncation is common to the numerator and the row sum and cancels).
-                const uint32_t e0 = __float_as_uint(ex2_approx(y0)), e1 = __float_as_uint(ex2_approx(y1));
-                qw[t] = ((e1 << 3) & 0xFFFF0000u) | (e0 >> 13);
-              } else {
-                qw[t] = poly ? pack_f16x2(exp2_fma(y0), exp2_fma(y1)) : pack_f16x2(ex2_approx(y0), ex2_approx(y1));
-              }
+              // which pairs of an 8-key chunk take the FMA-pipe exponential: POLY 1 -> pair 1; 2 -> pairs 1, 3; 3 -> 0, 1, 3
+              const bool poly = POLY == 1 ? (t == 1) : POLY == 2 ? (t & 1) : POLY == 3 ? (t != 2) : POLY == 4;
+              float y0, y1;
+              unpack2(ffma2(pack2u(s[i], s[i + 1]), sc2, poly ? nm_poly : nm_mufu), y0, y1);
+              qw[t] = poly ? exp2_h2(pack_f16x2(y0, y1)) : pack_f16x2(ex2_approx(y0), ex2_approx(y1));
             }
-            *reinterpret_cast<uint4*>(sPg + sw128_offset(r, 4 * h + c16)) = q;
+            st_shared_v4(sPg + p_off[c16], q);
           }
           if (pass > 0 || j == 0) break;
           const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
-          if (!__any_sync(0xffffffffu, m_new - m_run > kRescaleLog2)) break;
+          if (!__any_sync(0xffffffffu, m_new - m_run > kRescale5)) break;
           if (p.dbg && lane == 0) atomicAdd(p.dbg, 1ull);
           // rare: O_g,h must be stable -> this half's PV of the previous step has to be complete
           const float m_up = fmaxf(m_run, m_new);
@@ -1432,6 +1484,7 @@ static int launch_attn4(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
 }
 
 static unsigned long long* g_attn_dbg = nullptr;
+static int g_attn_poly = 2;   // pairs (of every 4) whose exponential runs on the FMA pipe in the head-dim-40 kernel
 
 }  // namespace a3d
 
@@ -1509,7 +1562,11 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   memset(&dev, 0, sizeof(dev));
   int qb1, qb2, qt1, qtiles, qrows, kb1, kb2, kt1, ktiles, krows;
   if (int r = tile_geom(a->q, &qb1, &qb2, &qt1, &qtiles, &qrows)) return r;
-  if (int r = tile_geom(a->k, &kb1, &kb2, &kt1, &ktiles, &krows)) return r;
+  if (d == 160) {   // 128-key steps (v1 kernel); head_dim 40 / 80 use 64-key steps and set their own key geometry (ragged ok)
+    if (int r = tile_geom(a->k, &kb1, &kb2, &kt1, &ktiles, &krows)) return r;
+  } else {
+    kb1 = kb2 = kt1 = ktiles = krows = 0;
+  }
   dev.q_tiles = qtiles; dev.kv_tiles = ktiles; dev.rows_q = qrows; dev.rows_k = krows;
   dev.heads = a->heads;
   dev.q_t1 = qt1; dev.q_box1 = qb1; dev.q_box2 = qb2; dev.q_e3 = a->q.e3;
@@ -1526,13 +1583,21 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
     return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
   const CUtensorMap *mq, *mk, *mv;
   if (int r = view_map(a->q, qb1, qb2, &mq)) return r;
-  if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
-  if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
+  mk = mv = nullptr;
+  if (d == 160) {
+    if (int r = view_map(a->k, kb1, kb2, &mk)) return r;
+    if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
+  }
   dim3 grid(qtiles, a->heads, batches);
   if (batches > 65535 || a->heads > 65535) return fail(A3D_EINVAL, "a3d_attention: grid too large");
   switch (d) {
     case 40:
-      return launch_attn5<40, 0>(dev, a, mq, grid, st);
+      switch (g_attn_poly) {
+        case 0: return launch_attn5<40, 0>(dev, a, mq, grid, st);
+        case 1: return launch_attn5<40, 1>(dev, a, mq, grid, st);
+        case 3: return launch_attn5<40, 3>(dev, a, mq, grid, st);
+        default: return launch_attn5<40, 2>(dev, a, mq, grid, st);
+      }
     case 80:
       return launch_attn4<80, 0>(dev, a, mq, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
@@ -1543,5 +1608,13 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
 // take the lazy-rescale branch (tests assert that adversarial inputs really exercise it); null switches it off
 extern "C" int a3d_debug_set_attn_trace(void* device_counter_u64) {
   a3d::g_attn_dbg = reinterpret_cast<unsigned long long*>(device_counter_u64);
+  return A3D_OK;
+}
+
+// tuning hook (tools/attn_variants.py): how many of every 4 score pairs of the head-dim-40 kernel take the FMA-pipe
+// exponential (0 = all MUFU ... 3); the product default is set where g_attn_poly is defined
+extern "C" int a3d_debug_set_attn_poly(int pairs_of_four) {
+  if (pairs_of_four < 0 || pairs_of_four > 3) return a3d::fail(A3D_EINVAL, "a3d_debug_set_attn_poly: 0..3");
+  a3d::g_attn_poly = pairs_of_four;
   return A3D_OK;
 }

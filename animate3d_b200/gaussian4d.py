@@ -177,11 +177,20 @@ class Gaussian4DModel(torch.nn.Module):
     """Registered in the reference as "gaussian-splatting-4d" (gaussian_4d.py:67)."""
 
     def __init__(self, xyz, scaling, rotation, opacity, features_dc, grid_size=((50, 50, 50, 8), (100, 100, 100, 16)),
-                 n_grid_dims: int = 16, n_neurons: int = 32, seed: int = 0, device="cuda", use_global_trans: bool = False):
+                 n_grid_dims: int = 16, n_neurons: int = 32, seed: int = 0, device="cuda", use_global_trans: bool = False,
+                 features_rest: Optional[torch.Tensor] = None, sh_degree: int = 0):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
-        for name, t in (("_xyz", xyz), ("_scaling", scaling), ("_rotation", rotation), ("_opacity", opacity), ("_features_dc", features_dc)):
+        features_dc = features_dc.reshape(features_dc.shape[0], 1, 3)
+        if features_rest is None:
+            features_rest = torch.zeros(features_dc.shape[0], 0, 3)
+        if features_rest.shape[1] != (sh_degree + 1) ** 2 - 1:
+            raise ValueError(f"features_rest holds {features_rest.shape[1]} coefficients, sh_degree {sh_degree} needs "
+                             f"{(sh_degree + 1) ** 2 - 1}")
+        for name, t in (("_xyz", xyz), ("_scaling", scaling), ("_rotation", rotation), ("_opacity", opacity),
+                        ("_features_dc", features_dc), ("_features_rest", features_rest)):
             self.register_buffer(name, t.float().to(device))      # frozen after load_ply (gaussian_4d.py:262-297)
+        self.max_sh_degree = sh_degree
         self.grids = torch.nn.ModuleList()
         for reso in grid_size:
             planes = torch.nn.ParameterList()
@@ -200,15 +209,22 @@ class Gaussian4DModel(torch.nn.Module):
         self.use_global_trans = use_global_trans
         if use_global_trans:   # gaussian_4d.py:129-142, zero-init last layers -> identity rotation / zero translation at start
             self.global_rot_network, self.global_trans_network = mlp(3), mlp(3)
-        self.active_sh_degree = 0
+        self.active_sh_degree = sh_degree      # load_ply sets active_sh_degree = max_sh_degree (gaussian_4d.py:306)
 
     @classmethod
-    def from_ply(cls, path: str, rot_x_degree: float = 0.0, rot_z_degree: float = 0.0, scale_factor: float = 1.0, **kw):
+    def from_ply(cls, path: str, rot_x_degree: float = 0.0, rot_z_degree: float = 0.0, scale_factor: float = 1.0,
+                 sh_degree: int = 0, **kw):
         """`load_ply` (gaussian_4d.py:177-306): static gaussians from a 3DGS PLY with the load-time rotate / scale."""
         from .io import load_gaussian_ply
-        g = load_gaussian_ply(path, rot_x_degree, rot_z_degree, scale_factor)
+        g = load_gaussian_ply(path, rot_x_degree, rot_z_degree, scale_factor, max_sh_degree=sh_degree)
         t = lambda k: torch.from_numpy(g[k])
-        return cls(t("_xyz"), t("_scaling"), t("_rotation"), t("_opacity"), t("_features_dc"), **kw)
+        return cls(t("_xyz"), t("_scaling"), t("_rotation"), t("_opacity"), t("_features_dc"), features_rest=t("_features_rest"),
+                   sh_degree=sh_degree, **kw)
+
+    @property
+    def get_features(self):
+        """GaussianBaseModel.get_features: cat(features_dc, features_rest) -> [P, (deg+1)^2, 3]."""
+        return torch.cat([self._features_dc, self._features_rest], dim=1)
 
     @property
     def get_opacity(self):

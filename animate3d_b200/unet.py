@@ -28,6 +28,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from .modules import attn_processors_of, build_tree
 from .unet_config import UNetConfig, key_plan, sinusoidal_pe, up_plan
 
 HALF = torch.float16
@@ -101,14 +102,19 @@ class _Lin:
         return o
 
 
-class MVUNetMotionModel:
+class MVUNetMotionModel(torch.nn.Module):
     """Drop-in for the reference class on the inference path (eval mode, no grad -- the reference never back-propagates
-    through the UNet: animatemv_guidance.py:422, pipeline.py:758)."""
+    through the UNet: animatemv_guidance.py:422, pipeline.py:758).
+
+    It IS an nn.Module: its parameter tree carries the reference's state-dict keys (fp32 masters on the device, see
+    modules.py), `attn_processors` / `set_attn_processor` / `from_unet2d` / `.to()` / `.config` behave like the reference's.
+    The forward does not execute those modules one by one: `_prepare()` repacks them into fused fp16 operands once."""
 
     def __init__(self, config: Optional[UNetConfig] = None, device: str = "cuda", view_group=None, **kwargs):
         """view_group: a torch.distributed process group whose ranks each hold ONE view of the same prompts (SURVEY 8e,
         "views span ranks").  Everything stays local except the cross-view attentions, whose K/V are all-gathered over the
         group (NCCL over NVLink); forward() is then called with the local view only and num_views=1."""
+        super().__init__()
         self.cfg = config or UNetConfig(**kwargs)
         self.view_group = view_group
         self.view_world = 1
@@ -116,8 +122,10 @@ class MVUNetMotionModel:
             import torch.distributed as dist
             self.view_world = dist.get_world_size(view_group)
         self.config = self.cfg        # diffusers-style attribute used by the pipeline (`unet.config.in_channels`)
-        self.device = torch.device(device)
-        self.dtype = HALF
+        self._device = torch.device(device)
+        build_tree(self, self.cfg, self._device)          # parameters / buffers under the reference's key names
+        self._loaded = set()                              # keys that received weights (the engine refuses to run on defaults)
+        self._masters_dropped = False
         self._prepared = False
         self._bufs: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
@@ -126,39 +134,163 @@ class MVUNetMotionModel:
         self.gemm_impl = L.IMPL_AUTO
         self.attn_impl = L.IMPL_AUTO
         self.launches = 0            # kernel launches issued by the last eager run (bench's gpu_launches claim)
+        self.eval()
+        self.requires_grad_(False)
+
+    # ------------------------------------------------------------------------------------------------ module surface
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return HALF                   # compute dtype of the engine (fp16 operands, fp32 accumulation)
+
+    def to(self, *args, **kwargs):
+        """Device moves relocate the fp32 masters and invalidate the packed operands; dtype requests are accepted and ignored
+        (the reference calls `.to(torch.float16)`, animatemv_guidance.py:275 -- that IS the engine's operand type)."""
+        device = kwargs.get("device")
+        for a in args:
+            if isinstance(a, (str, torch.device)):
+                device = a
+            elif isinstance(a, torch.Tensor):
+                device = a.device
+        if device is not None and torch.device(device) != self._device:
+            if torch.device(device).type != "cuda":
+                raise RuntimeError("MVUNetMotionModel runs on an sm_100a device only; there is no CPU path")
+            super().to(device)
+            self._device = torch.device(device)
+            self._prepared = False
+            self._bufs.clear(); self._graphs.clear(); self._static.clear()
+        return self
+
+    def half(self):
+        return self
+
+    def float(self):
+        return self
+
+    @property
+    def attn_processors(self):
+        """unet_motion_mv_model.py:441-462: {"<path>.processor": processor module} for all 74 attention layers."""
+        return attn_processors_of(self)
+
+    def set_attn_processor(self, processor):
+        """unet_motion_mv_model.py:465-497.  Only the released wiring runs on the engine: a dict with one processor per layer,
+        each of the kind and geometry the released model uses there (modules.AttentionNode.set_processor checks both)."""
+        cur = self.attn_processors
+        if not isinstance(processor, dict):
+            raise ValueError("a single processor for all layers cannot express the released wiring (three processor kinds, "
+                             "inference.py:107-174); pass the dict built from `unet.attn_processors`")
+        if len(processor) != len(cur):
+            raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} does not match the"
+                             f" number of attention layers: {len(cur)}. Please make sure to pass {len(cur)} processor classes.")
+        unknown = [k for k in processor if k not in cur]
+        if unknown:
+            raise ValueError(f"unknown attention layers: {unknown[:3]}")
+        for name, module in self.named_modules():
+            if hasattr(module, "set_processor"):
+                key = f"{name}.processor"
+                new = processor[key]
+                if new is not cur[key]:
+                    module.set_processor(new)
+                    self._loaded.update(f"{key}.{k}" for k in cur[key].state_dict())
+        self._prepared = False
+
+    @classmethod
+    def from_unet2d(cls, unet, motion_adapter=None, load_weights: bool = True, device: str = "cuda", **kwargs):
+        """unet_motion_mv_model.py:275-368: geometry from the 2-D multi-view UNet's config, its weights copied, motion modules
+        taken from the adapter.  Unlike the reference the result already carries the released processors (inference.py:107-174
+        installs them right afterwards): to_q_i2v starts as a copy of to_q and to_out_i2v at zero (inference.py:161-165)."""
+        src = unet.config
+        get = (lambda k, d=None: src.get(k, d)) if hasattr(src, "get") else (lambda k, d=None: getattr(src, k, d))
+        heads = get("num_attention_heads") or get("attention_head_dim")
+        heads = heads[0] if isinstance(heads, (tuple, list)) else heads
+        cfg_kw = dict(in_channels=get("in_channels", 4), out_channels=get("out_channels", 4),
+                      block_out_channels=tuple(get("block_out_channels")), layers_per_block=get("layers_per_block", 2),
+                      norm_num_groups=get("norm_num_groups", 32), norm_eps=get("norm_eps", 1e-5),
+                      cross_attention_dim=get("cross_attention_dim", 768), num_attention_heads=heads,
+                      down_has_attn=tuple("CrossAttn" in t for t in get("down_block_types")))
+        if motion_adapter is not None:
+            mc = motion_adapter.config
+            mget = (lambda k, d=None: mc.get(k, d)) if hasattr(mc, "get") else (lambda k, d=None: getattr(mc, k, d))
+            cfg_kw.update(motion_num_attention_heads=mget("motion_num_attention_heads", 8),
+                          motion_max_seq_length=mget("motion_max_seq_length", 32))
+            if mget("conv_in_channels"):
+                raise NotImplementedError("PIA adapters (conv_in_channels) are not part of Animate3D")
+        cfg_kw.update(kwargs)
+        model = cls(UNetConfig(**cfg_kw), device=device)
+        if not load_weights:
+            return model
+        sd = {k: v for k, v in unet.state_dict().items() if k in key_plan(model.cfg)}
+        if motion_adapter is not None:     # load_motion_modules: same "<block>.motion_modules.*" key names
+            sd.update({k: v for k, v in motion_adapter.state_dict().items() if k in key_plan(model.cfg)})
+        for k in list(sd):                  # the I2V branch of every spatial attn1 starts from to_q (inference.py:161-165)
+            if k.endswith("attn1.to_q.weight") and ".attentions." in k:
+                sd.setdefault(k.replace("attn1.to_q.weight", "attn1.processor.to_q_i2v.weight"), sd[k])
+        model.load_state_dict(sd, strict=False)
+        for k in key_plan(model.cfg):        # zero-initialised branches count as initialised
+            if k.endswith(("to_out_i2v.weight", "to_out_i2v.bias", "time_pos_embed.pe", "mix_factor")):
+                model._loaded.add(k)
+        return model
+
+    def _load_ip_adapter_weights(self, state_dict):
+        """diffusers' loader hook used by animatediff/utils/util.py::load_ip_adapter: {"image_proj": {...}, "ip_adapter": {...}}
+        -> encoder_hid_proj.image_projection_layers.0.* and the 16 attn2 processors' to_k_ip / to_v_ip."""
+        sds = state_dict if isinstance(state_dict, (list, tuple)) else [state_dict]
+        if len(sds) != 1:
+            raise NotImplementedError("one IP-Adapter (the released model's) is supported")
+        sd = sds[0]
+        ip = "encoder_hid_proj.image_projection_layers.0"
+        new = {f"{ip}.image_embeds.weight": sd["image_proj"]["proj.weight"], f"{ip}.image_embeds.bias": sd["image_proj"]["proj.bias"],
+               f"{ip}.norm.weight": sd["image_proj"]["norm.weight"], f"{ip}.norm.bias": sd["image_proj"]["norm.bias"]}
+        names = [n for n in self.attn_processors if n.endswith("attn2.processor") and ".attentions." in n]
+        # diffusers numbers the adapter's layers over ALL attn processors in definition order: attn2 slots are the odd ones
+        for i, n in enumerate(names):
+            new[f"{n}.to_k_ip.0.weight"] = sd["ip_adapter"][f"{2 * i + 1}.to_k_ip.weight"]
+            new[f"{n}.to_v_ip.0.weight"] = sd["ip_adapter"][f"{2 * i + 1}.to_v_ip.weight"]
+        self.load_state_dict(new, strict=False)
 
     # ------------------------------------------------------------------------------------------------ weights
     @staticmethod
     def expected_keys(cfg: Optional[UNetConfig] = None) -> List[str]:
         return list(key_plan(cfg or UNetConfig()).keys())
 
-    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
-        """Returns (missing_keys, unexpected_keys) like torch.  With strict=False a partial (motion-module-only)
-        checkpoint updates what it holds (inference.py:219-223)."""
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True, assign: bool = False):
+        """Returns torch's (missing_keys, unexpected_keys) pair.  With strict=False a partial (motion-module-only) checkpoint
+        updates what it holds (inference.py:219-223)."""
+        if self._masters_dropped:
+            raise RuntimeError("the fp32 masters were released (drop_reference_weights); build a new model to load weights")
+        res = super().load_state_dict({k: v for k, v in sd.items()}, strict=strict)
         plan = key_plan(self.cfg)
-        missing = [k for k in plan if k not in sd]
-        unexpected = [k for k in sd if k not in plan]
-        if strict and (missing or unexpected):
-            raise KeyError(f"state dict mismatch: {len(missing)} missing, {len(unexpected)} unexpected")
-        for k, v in sd.items():
-            if k in plan and tuple(v.shape) != tuple(plan[k]):
-                raise ValueError(f"{k}: shape {tuple(v.shape)} != {tuple(plan[k])}")
-        if not hasattr(self, "_sd"):
-            self._sd = {}
-        self._sd.update({k: v.detach().to(torch.float32) for k, v in sd.items() if k in plan})
+        self._loaded.update(k for k in sd if k in plan)
         self._prepared = False
-        return missing, unexpected
+        return res
 
-    def state_dict(self):
-        return dict(self._sd)
+    def drop_reference_weights(self):
+        """Free the fp32 master copies (6 GB for the released geometry) once the packed operands exist; `state_dict()` is then
+        unavailable.  bench.py uses it to keep the working set to what a serving process would hold."""
+        if not self._prepared:
+            self._prepare()
+        for p in list(self.parameters()) + list(self.buffers()):
+            p.data = torch.empty(0, device=p.device, dtype=p.dtype)
+        self._masters_dropped = True
+
+    def state_dict(self, *args, **kwargs):
+        if self._masters_dropped:
+            raise RuntimeError("the fp32 masters were released (drop_reference_weights)")
+        return super().state_dict(*args, **kwargs)
 
     def _prepare(self):
         """Repack the reference-layout fp32 weights into the fused fp16 operands the kernels consume."""
         L.load()
-        sd, cfg, dev = self._sd, self.cfg, self.device
-        miss = [k for k in key_plan(cfg) if k not in sd]
+        if self._masters_dropped:
+            raise RuntimeError("the fp32 masters were released; the packed operands cannot be rebuilt")
+        cfg, dev = self.cfg, self.device
+        miss = [k for k in key_plan(cfg) if k not in self._loaded]
         if miss:
             raise KeyError(f"cannot run: {len(miss)} weights missing, e.g. {miss[:3]}")
+        sd = {k: v.detach() for k, v in torch.nn.Module.state_dict(self).items()}
         W: Dict[str, object] = {}
         heads = cfg.num_attention_heads
         f32 = lambda k: sd[k].to(dev, torch.float32).contiguous()
@@ -677,4 +809,3 @@ class MVUNetMotionModel:
         out = st["out"].clone()
         return UNet3DConditionOutput(sample=out) if return_dict else (out,)
 
-    __call__ = forward

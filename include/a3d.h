@@ -266,6 +266,9 @@ int a3d_arap(const float* nodes, int Nt, int Nv, const int32_t* nbr, int K, cons
 /* debug hook: a device uint64 counter the tcgen05 attention kernels bump once per (warp, key step) that takes the
    lazy-rescale branch of the single-pass softmax (NULL = off; tests use it to prove adversarial inputs reach that branch) */
 int a3d_debug_set_attn_trace(void* device_counter_u64);
+/* tuning hook: number (0..3) of every 4 score pairs whose exponential the head-dim-40 attention kernel evaluates on the FMA
+   pipe (half2 polynomial) instead of MUFU.EX2; see csrc/a3d_attn.cu "softmax arithmetic of the v5 kernel" */
+int a3d_debug_set_attn_poly(int pairs_of_four);
 /* same for the tcgen05 GEMM: per-tile timestamps of CTA 0 (epilogue warp 0 and the MMA-issuing thread) */
 int a3d_debug_set_gemm_trace(void* device_buffer_1024_int64);
 

@@ -17,7 +17,7 @@ model = MVUNetMotionModel(cfg)
 model.use_cuda_graph = False
 model.load_state_dict(random_state_dict(cfg, 0, "cuda"))
 model._prepare()
-model._sd = {}
+model.drop_reference_weights()
 sched = DDIMScheduler()
 sched.set_timesteps(25)
 pipe = AnimateDiffMVI2VPipeline(unet=model, scheduler=sched)

@@ -46,9 +46,9 @@ def cameras(n_views=4, n_frames=16, seed=0, device="cuda"):
 
 
 def run(P=50000, H=512, W=512, iters=5):
-    from animate3d_b200.renderer import Gaussian4DBatchRenderer
+    from animate3d_b200.renderer import make_renderer
     model = synthetic_model(P)
-    r = Gaussian4DBatchRenderer(model)
+    r = make_renderer(model)
     c2w, fovy, ts = cameras()
     batch = {"c2w": c2w, "fovy": fovy, "width": W, "height": H, "timestamps": ts, "do_guidance": True, "do_reconstruction": True}
     target = torch.rand(c2w.shape[0], H, W, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
