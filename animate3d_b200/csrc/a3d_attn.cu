@@ -30,7 +30,10 @@ struct AttnDev {
   int64_t os1, os2, os3, os4;
   int accumulate;
   float out_scale;
-  unsigned long long* dbg;   // debug (null in production): dbg[0] counts (warp, step) pairs that took the lazy-rescale branch
+  int early_test;            // head-dim-40 kernel: non-blocking barrier tests one step ahead (see the step loop)
+  int xu_conc;               // head-dim-40 kernel: warps of an SM sub-partition allowed in their exponential phase at once (0 = free)
+  unsigned long long* dbg;   // debug (null in production): dbg[0] counts (warp, step) pairs that took the lazy-rescale branch;
+                             // dbg[8 + (w*32 + j)*8 + k]: clock64 timeline of 4 softmax warps of CTA (0,0,0) (head-dim-40 kernel)
 };
 
 constexpr float kRescaleLog2 = 8.0f;
@@ -767,6 +770,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   uint64_t* pv_done = p_full + 8;              // [2][2][2]
   uint64_t* o_full = pv_done + 8;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint32_t* xu_turn = tmem_slot + 4;           // [4 sub-partitions] exponential phases completed (XU turn-taking)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -783,6 +787,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
+  if (threadIdx.x < 4) xu_turn[threadIdx.x] = 0;
   if (warp == 18 && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
@@ -928,16 +933,27 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       uint32_t p_off[4];      // this thread's four 16-byte P chunks of a step (128B-swizzled row r, chunks 4h .. 4h+3)
 #pragma unroll
       for (int c16 = 0; c16 < 4; ++c16) p_off[c16] = sw128_offset(r, 4 * h + c16);
+      const int nk = has1 ? 4 : 2, kslot = has1 ? 2 * g + h : h;          // warps of this sub-partition in the XU rotation
+      const uint32_t turn_addr = smem_u32(xu_turn + quad);
       const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2);
       const int oc0 = h ? Cfg::kOChunks0 : 0, oc1 = h ? Cfg::kOChunks : Cfg::kOChunks0;
+      // "is S(j+1) there" / "are the P columns of step j+1 free" are TESTED (non-blocking) while step j's exponentials run and
+      // only waited for when the test failed: an mbarrier try_wait costs ~100-190 cycles even on a completed phase, and the
+      // four warps of a sub-partition pay it in lockstep while the XU pipe idles (profiles/r02_attn_timeline.txt)
+      bool s_ok = false, p_ok = true;
       for (int j = 0; j < n; ++j) {
         const int valid = ((j == n - 1) ? p.rows_k : rows_tile) - 32 * h;   // valid keys among this half's 32 columns
         const int b = 2 * g + (j & 1);
-        mbar_wait(&s_full[b], (j >> 1) & 1);
+        // debug timeline (tools/attn_timeline.py): the four softmax warps of SM sub-partition 0 of CTA (0,0,0), 32 steps
+        const bool tr = p.dbg && j < 32 && quad == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        unsigned long long* trow = p.dbg + 8 + ((warp >> 2) * 32 + j) * 8;
+        if (tr) trow[0] = clock64();
+        if (!(p.early_test && s_ok)) mbar_wait(&s_full[b], (j >> 1) & 1);
         tc_fence_after();
         uint32_t s[32];
         tmem_ld32(tmem_base + lane_addr + b * 64 + 32 * h, s);
         tmem_wait_ld();
+        if (tr) trow[1] = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[b]);   // S buffer may be overwritten by QK^T(j+2)
@@ -956,7 +972,21 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           m_run = fmaxf(fmaxf(mx0, mx1) * p.scale_log2, -1.0e30f);
         }
         const uint32_t sPg = sP_u32 + b * Cfg::kPBox;
-        if (j >= 2) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);   // P columns of step j-2 consumed (long ago)
+        if (j >= 2 && !(p.early_test && p_ok)) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);   // P columns of step j-2 consumed
+        if (p.early_test) {   // tests for step j+1, consumed at its top
+          s_ok = j + 1 < n && mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1);
+          p_ok = j + 1 < 2 || mbar_test(&my_pv_done[(j + 1) & 1], ((j - 1) >> 1) & 1);
+        }
+        // XU turn-taking: the softmax warps of an SM sub-partition share ONE MUFU pipe.  Left alone they fall into lockstep
+        // (processor sharing makes them finish their exponentials together) and then sit in barrier / fence latency together
+        // while the pipe idles -- profiles/r02_attn_timeline.txt.  A per-sub-partition ticket makes them take the pipe in a
+        // fixed rotation, at most `p.xu_conc` warps at a time, so one warp's publish / wait phase overlaps the others'
+        // exponentials.
+        if (p.xu_conc > 0) {
+          const uint32_t need = (uint32_t)(nk * j + kslot);
+          while (ld_volatile_shared(turn_addr) + (uint32_t)p.xu_conc <= need) {}
+        }
+        if (tr) trow[2] = clock64();
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
           // Single pass with a STALE stabiliser (the running max of the previous steps); this step's max is accumulated in
@@ -1002,10 +1032,16 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           tmem_wait_st();
           m_run = m_up;
         }
+        if (p.xu_conc > 0) {
+          __syncwarp();
+          if (lane == 0) red_add_shared(turn_addr, 1u);
+        }
+        if (tr) trow[3] = clock64();
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&my_p_full[j & 1]);
+        if (tr) trow[4] = clock64();
       }
       // ---- epilogue: merge the two halves' partial softmax states; this half writes its chunks of the rows
       mbar_wait(&o_full[g], 0);
@@ -1484,7 +1520,9 @@ static int launch_attn4(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
 }
 
 static unsigned long long* g_attn_dbg = nullptr;
-static int g_attn_poly = 2;   // pairs (of every 4) whose exponential runs on the FMA pipe in the head-dim-40 kernel
+static int g_attn_poly = 0;   // pairs (of every 4) whose exponential runs on the FMA pipe in the head-dim-40 kernel
+static int g_attn_xu_conc = 0;
+static int g_attn_early = 1;
 
 }  // namespace a3d
 
@@ -1579,6 +1617,8 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   dev.accumulate = a->accumulate;
   dev.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
   dev.dbg = g_attn_dbg;
+  dev.xu_conc = g_attn_xu_conc;
+  dev.early_test = g_attn_early;
   if ((a->os1 | a->os2 | a->os3 | a->os4) % 8 || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
   const CUtensorMap *mq, *mk, *mv;
@@ -1606,7 +1646,7 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
 
 // debug hook (not part of the product path): device counter the softmax warps of the tcgen05 kernels bump whenever they
 // take the lazy-rescale branch (tests assert that adversarial inputs really exercise it); null switches it off
-extern "C" int a3d_debug_set_attn_trace(void* device_counter_u64) {
+extern "C" int a3d_debug_set_attn_trace(void* device_counter_u64) {   // buffer of >= 8 + 4*32*8 uint64
   a3d::g_attn_dbg = reinterpret_cast<unsigned long long*>(device_counter_u64);
   return A3D_OK;
 }
@@ -1614,7 +1654,11 @@ extern "C" int a3d_debug_set_attn_trace(void* device_counter_u64) {
 // tuning hook (tools/attn_variants.py): how many of every 4 score pairs of the head-dim-40 kernel take the FMA-pipe
 // exponential (0 = all MUFU ... 3); the product default is set where g_attn_poly is defined
 extern "C" int a3d_debug_set_attn_poly(int pairs_of_four) {
-  if (pairs_of_four < 0 || pairs_of_four > 3) return a3d::fail(A3D_EINVAL, "a3d_debug_set_attn_poly: 0..3");
-  a3d::g_attn_poly = pairs_of_four;
+  // bits 0-3: polynomial pairs (0..3); bits 4-7: XU turn-taking concurrency (0 = off, 1..4)
+  const int poly = pairs_of_four & 15, conc = (pairs_of_four >> 4) & 15;
+  if (poly > 3 || conc > 4) return a3d::fail(A3D_EINVAL, "a3d_debug_set_attn_poly: poly 0..3, concurrency 0..4");
+  a3d::g_attn_poly = poly;
+  a3d::g_attn_xu_conc = conc;
+  a3d::g_attn_early = (pairs_of_four >> 8) & 1;
   return A3D_OK;
 }

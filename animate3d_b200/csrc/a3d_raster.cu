@@ -108,6 +108,26 @@ raster_render_backward_kernel(RasterDev a, RasterWs ws, const float* __restrict_
   const int tid = threadIdx.y * kTile + threadIdx.x;
   const int lane = tid & 31;
   int contributor = total;   // 1-based index (in list order) of the entry about to be processed, counted from the back
+  // where lane 2k sends the warp total of value k (see the reduction below); odd lanes and k >= 10 have no target
+  float* tgt_base = nullptr;
+  size_t tgt_off = cbase;
+  int tgt_mul = 1, tgt_add = 0;
+  if (!(lane & 1)) {
+    switch (lane >> 1) {
+      case 0: tgt_base = ws.g_mean2d; tgt_mul = 2; tgt_add = 0; break;
+      case 1: tgt_base = ws.g_mean2d; tgt_mul = 2; tgt_add = 1; break;
+      case 2: tgt_base = ws.g_conic; tgt_mul = 3; tgt_add = 0; break;
+      case 3: tgt_base = ws.g_conic; tgt_mul = 3; tgt_add = 1; break;
+      case 4: tgt_base = ws.g_conic; tgt_mul = 3; tgt_add = 2; break;
+      case 5: tgt_base = dL_dopacity; tgt_off = 0; break;                 // opacities are shared by the cameras: [P]
+      case 6: tgt_base = ws.g_rgb; tgt_mul = 3; tgt_add = 0; break;
+      case 7: tgt_base = ws.g_rgb; tgt_mul = 3; tgt_add = 1; break;
+      case 8: tgt_base = ws.g_rgb; tgt_mul = 3; tgt_add = 2; break;
+      case 9: tgt_base = ws.g_depth; break;
+      default: break;
+    }
+  }
+  const int warp_last = __reduce_max_sync(0xffffffffu, last_contributor);   // entries behind every pixel's last one: skip
   for (int r = 0; r < rounds; ++r) {
     __syncthreads();
     const int progress = r * kBlockPix + tid;   // back to front
@@ -121,6 +141,7 @@ raster_render_backward_kernel(RasterDev a, RasterWs ws, const float* __restrict_
     __syncthreads();
     const int n = (total - r * kBlockPix) < kBlockPix ? (total - r * kBlockPix) : kBlockPix;
     for (int j = 0; j < n; ++j, --contributor) {
+      if (contributor > warp_last) continue;
       SplatGrad g;
       g.dmx = g.dmy = g.dconA = g.dconB = g.dconC = g.dopac = g.ddepth = 0.f;
       g.dcol[0] = g.dcol[1] = g.dcol[2] = 0.f;
@@ -140,18 +161,23 @@ raster_render_backward_kernel(RasterDev a, RasterWs ws, const float* __restrict_
         }
       }
       if (!__any_sync(0xffffffffu, active)) continue;
-      const float v0 = warp_sum(g.dmx), v1 = warp_sum(g.dmy), v2 = warp_sum(g.dconA), v3 = warp_sum(g.dconB), v4 = warp_sum(g.dconC);
-      const float v5 = warp_sum(g.dopac), v6 = warp_sum(g.dcol[0]), v7 = warp_sum(g.dcol[1]), v8 = warp_sum(g.dcol[2]);
-      const float v9 = warp_sum(g.ddepth);
-      if (lane == 0) {
-        const uint32_t id = s_id[j];
-        const size_t gi = cbase + id;
-        atomicAdd(ws.g_mean2d + 2 * gi, v0); atomicAdd(ws.g_mean2d + 2 * gi + 1, v1);
-        atomicAdd(ws.g_conic + 3 * gi, v2); atomicAdd(ws.g_conic + 3 * gi + 1, v3); atomicAdd(ws.g_conic + 3 * gi + 2, v4);
-        if (dL_dopacity) atomicAdd(dL_dopacity + id, v5);
-        atomicAdd(ws.g_rgb + 3 * gi, v6); atomicAdd(ws.g_rgb + 3 * gi + 1, v7); atomicAdd(ws.g_rgb + 3 * gi + 2, v8);
-        atomicAdd(ws.g_depth + gi, v9);
+      // Transposing butterfly: the 10 partial gradients (padded to 16) of the warp's 32 pixels are reduced with 16 shuffles
+      // instead of 10 x 5; afterwards lane 2k holds the warp total of value k and lanes 0, 2, ..., 18 issue their ONE atomic
+      // in parallel (the upstream kernel: one atomic per pixel and value; round 1 here: 50 shuffles + 10 serial atomics).
+      float v[16] = {g.dmx, g.dmy, g.dconA, g.dconB, g.dconC, g.dopac, g.dcol[0], g.dcol[1], g.dcol[2], g.ddepth,
+                     0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int o = 16, cnt = 8; cnt >= 1; o >>= 1, cnt >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+          const float send = upper ? v[i] : v[i + cnt];
+          const float keep = upper ? v[i + cnt] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
       }
+      const float total = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+      if (tgt_base) atomicAdd(tgt_base + tgt_mul * (tgt_off + (size_t)s_id[j]) + tgt_add, total);
     }
   }
 }
@@ -193,9 +219,43 @@ static int check_args(const a3d_raster_args* a, long long cap) {
   return 0;
 }
 
+// ---- optional per-stage timing (bench.py's splat roofline): CUDA events recorded on the caller's stream at stage boundaries
+constexpr int kStages = 8;   // 0 preprocess, 1 scan+counts+duplicate, 2 radix sort, 3 ranges, 4 render fwd, 5 render bwd, 6 preprocess bwd
+static bool g_timing = false;
+static cudaEvent_t g_ev[kStages + 2];
+static bool g_ev_init = false, g_fwd_rec = false, g_bwd_rec = false;
+static void stamp(int i, cudaStream_t st) {
+  if (g_timing) cudaEventRecord(g_ev[i], st);
+}
+
 }  // namespace a3d
 
 using namespace a3d;
+
+extern "C" int a3d_debug_raster_timing(int enable) {
+  if (enable && !g_ev_init) {
+    for (int i = 0; i < kStages + 2; ++i) A3D_CUDA_CHECK(cudaEventCreate(&g_ev[i]));
+    g_ev_init = true;
+  }
+  g_timing = enable != 0;
+  g_fwd_rec = g_bwd_rec = false;
+  return A3D_OK;
+}
+
+// ms per stage of the LAST forward (0..4) and backward (5, 6) issued with timing enabled; synchronises on the recorded events
+extern "C" int a3d_debug_raster_stage_ms(float* out_host8) {
+  if (!g_ev_init || !out_host8) return fail(A3D_EINVAL, "a3d_debug_raster_stage_ms: timing was never enabled");
+  for (int i = 0; i < kStages; ++i) out_host8[i] = 0.f;
+  if (g_fwd_rec) {
+    A3D_CUDA_CHECK(cudaEventSynchronize(g_ev[5]));
+    for (int i = 0; i < 5; ++i) A3D_CUDA_CHECK(cudaEventElapsedTime(&out_host8[i], g_ev[i], g_ev[i + 1]));
+  }
+  if (g_bwd_rec) {
+    A3D_CUDA_CHECK(cudaEventSynchronize(g_ev[8]));
+    for (int i = 5; i < 7; ++i) A3D_CUDA_CHECK(cudaEventElapsedTime(&out_host8[i], g_ev[i + 1], g_ev[i + 2]));
+  }
+  return A3D_OK;
+}
 
 extern "C" size_t a3d_raster_workspace_bytes(int P, int H, int W, int num_cams, int64_t max_rendered) {
   const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
@@ -220,20 +280,27 @@ extern "C" int a3d_raster_forward(const a3d_raster_args* a, float* color, float*
   const int n = a->num_cams * a->P;
   A3D_CUDA_CHECK(cudaMemsetAsync(ws.keys_a, 0xFF, (size_t)max_rendered * 8, st));
   A3D_CUDA_CHECK(cudaMemsetAsync(ws.ranges, 0, (size_t)total_tiles * 8, st));
+  stamp(0, st);
   launch_preprocess(d, ws, radii, st);
   A3D_LAUNCH_CHECK();
+  stamp(1, st);
   size_t tb = ws.cub_bytes;
   A3D_CUDA_CHECK(cub::DeviceScan::InclusiveSum(ws.cub_temp, tb, ws.tiles, ws.offsets, n, st));
   launch_counts(ws, a->P, a->num_cams, max_rendered, st);
   launch_duplicate(d, ws, gx, gx * gy, max_rendered, st);
   A3D_LAUNCH_CHECK();
+  stamp(2, st);
   tb = ws.cub_bytes;
   A3D_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ws.cub_temp, tb, ws.keys_a, ws.keys_b, ws.vals_a, ws.vals_b, (int)max_rendered, 0,
                                                  end_bit, st));
+  stamp(3, st);
   launch_ranges(ws, max_rendered, total_tiles, st);
+  stamp(4, st);
   dim3 grid(gx, gy, a->num_cams), block(kTile, kTile);
   raster_render_forward_kernel<<<grid, block, 0, st>>>(d, ws, color, depth, alpha);
   A3D_LAUNCH_CHECK();
+  stamp(5, st);
+  g_fwd_rec = g_timing;
   if (num_rendered_host)
     A3D_CUDA_CHECK(cudaMemcpyAsync(num_rendered_host, ws.counters, sizeof(long long) * (a->num_cams + 2), cudaMemcpyDeviceToHost, st));
   return A3D_OK;
@@ -260,10 +327,14 @@ extern "C" int a3d_raster_backward(const a3d_raster_args* a, const float* dL_dco
   A3D_CUDA_CHECK(cudaMemsetAsync(ws.g_depth, 0, n * 4, st));
   A3D_CUDA_CHECK(cudaMemsetAsync(ws.g_rgb, 0, n * 12, st));
   dim3 grid(gx, gy, a->num_cams), block(kTile, kTile);
+  stamp(6, st);
   raster_render_backward_kernel<<<grid, block, 0, st>>>(d, ws, dL_dcolor, dL_ddepth, dL_dalpha, dL_dopacity);
   A3D_LAUNCH_CHECK();
+  stamp(7, st);
   launch_preprocess_backward(d, ws, radii, dL_dmeans3D, dL_dscales, dL_drotations, dL_dcolors, dL_dshs, dL_dmeans2D, st);
   A3D_LAUNCH_CHECK();
+  stamp(8, st);
+  g_bwd_rec = g_timing;
   return A3D_OK;
 }
 

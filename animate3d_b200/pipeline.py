@@ -118,6 +118,35 @@ class AnimateDiffMVI2VPipeline:
         torch.cuda.current_stream().synchronize()
         return out_host
 
+    def denoise_step_sharded(self, latents_local: torch.Tensor, t: int, prompt_embeds_local: torch.Tensor,
+                             camera_local: torch.Tensor, image_embeds_local: torch.Tensor, first_frame_local: torch.Tensor,
+                             guidance_scale: float, cfg_group=None, num_views_local: int = 4,
+                             i2v_cond_time_zero: bool = False) -> torch.Tensor:
+        """One denoise step of ONE prompt spread over ranks: this rank owns `num_views_local` views (all of them,
+        or one when `self.unet.view_group` shards the views) and either both CFG branches (cfg_group None: inputs carry the
+        (uncond, cond) duplication) or one of them (cfg_group of size 2: rank 0 = uncond, rank 1 = cond).  Collectives: the
+        K|V all-gathers inside the UNet (view group) and ONE all-gather of the noise prediction over the CFG group
+        (n_local x 4 x F x h x w fp32 = 0.25 MB per view).  The latents stay sharded by view across steps."""
+        nloc = latents_local.shape[0]
+        if cfg_group is None:
+            x = torch.cat([latents_local, latents_local], 0)
+        else:
+            x = latents_local
+        eps = self.unet(x, t, prompt_embeds_local, camera=camera_local, added_cond_kwargs={"image_embeds": image_embeds_local},
+                        num_views=num_views_local, i2v_cond_time_zero=i2v_cond_time_zero).sample
+        if cfg_group is not None:
+            import torch.distributed as dist
+            eps2 = self._eps2 if getattr(self, "_eps2", None) is not None and self._eps2.shape[0] == 2 * nloc else None
+            if eps2 is None:
+                eps2 = self._eps2 = torch.empty(2 * nloc, *eps.shape[1:], device=eps.device, dtype=eps.dtype)
+            dist.all_gather_into_tensor(eps2.view(-1), eps.contiguous().view(-1), group=cfg_group)
+            eps = eps2
+        a_t, a_p = self.scheduler.alphas_for(int(t))
+        _, c, f, h, w = latents_local.shape
+        ops.ddim_cfg_step(latents_local, eps.contiguous(), first_frame_local.contiguous(), nloc, c, f, h * w, guidance_scale, a_t,
+                          a_p, uncond_first=True)
+        return latents_local
+
     # -------------------------------------------------------------------------------------------- full sampler
     def _apply_free_init(self, latents, it, num_inference_steps, generator):
         """FreeInitMixin._apply_free_init on frames 1.. (pipeline.py:990-992)."""

@@ -35,6 +35,7 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 _cap_hint = {}
+last_num_rendered = 0      # (tile, gaussian) pairs of the most recent forward (diagnostics / bench roofline)
 
 
 def _pack_cams(settings: Sequence[GaussianRasterizationSettings], device) -> torch.Tensor:
@@ -93,7 +94,9 @@ class _RasterizeBatch(torch.autograd.Function):
             if int(counts[ncam + 1]) == 0:
                 break
             cap = int(total * 1.25) + 1024                 # overflowed: grow and redo
-        _cap_hint[key] = max(int(total * 1.3) + 1024, 1 << 16)
+        global last_num_rendered
+        last_num_rendered = total
+        _cap_hint[key] = max(int(total * 1.08) + 1024, 1 << 16)   # the radix sort runs over the capacity: keep the slack small
         ctx.save_for_backward(means3D, scales, rotations, opacities, shs, colors_precomp, cams_t, radii, alpha, ws)
         ctx.meta = (meta, cap, nbytes, P, ncam)
         ctx.m2_shape = None if means2D is None else tuple(means2D.shape)

@@ -81,6 +81,10 @@ class Gaussian4DBatchRenderer:
                     scales_t = torch.where(keep, torch.exp(pc._scaling)[None], scales_t)
                     rots_t = torch.where(keep, torch.nn.functional.normalize(pc._rotation, dim=-1)[None], rots_t)
             means, scales, rots = means_t[inverse], scales_t[inverse], rots_t[inverse]
+        # per-camera tensors that are ON the autograd path (callers read / retain_grad `out["means3D"][i]` like the reference's
+        # per-camera `means3D`): unbind first, render from the re-stacked batch
+        means_l, scales_l, rots_l = list(means.unbind(0)), list(scales.unbind(0)), list(rots.unbind(0))
+        means, scales, rots = torch.stack(means_l), torch.stack(scales_l), torch.stack(rots_l)
         # ---- reconstruction-stage gradient gating (147-154): ~10 % of the gaussians of every camera keep their gradient
         if not do_guidance:
             mask = (torch.rand(bs, P, 1, device=dev) < 0.1).float()
@@ -91,9 +95,7 @@ class Gaussian4DBatchRenderer:
         if not do_reconstruction:
             means_in = means_in.detach()                                                          # 161
         # ---- screen-space points: one tensor per camera, like the reference's list of `screenspace_points`
-        vsp = [torch.zeros(P, 3, device=dev, requires_grad=True) + 0 for _ in range(bs)]
-        for v in vsp:
-            v.retain_grad()
+        vsp = [v.requires_grad_() for v in torch.zeros(bs, P, 3, device=dev).unbind(0)]      # leaves: .grad is populated
         m2 = torch.stack(vsp, 0)
         opacity = pc.get_opacity
         shs = colors = None
@@ -128,7 +130,7 @@ class Gaussian4DBatchRenderer:
                 color = color.index_copy(0, sel, c_); depth = depth.index_copy(0, sel, d_)
                 alpha = alpha.index_copy(0, sel, a_); radii = radii.index_copy(0, sel, r_)
         return {"render": color.clamp(0, 1), "depth": depth, "mask": alpha, "viewspace_points": vsp, "radii": radii,
-                "means3D": means, "scales": scales, "rotations": rots, "opacities": opacity}
+                "means3D": means_l, "scales": scales_l, "rotations": rots_l, "opacities": opacity}
 
     def batch_forward(self, batch: Dict) -> Dict:
         """batch: c2w [bs,4,4], fovy [bs], width, height, timestamps [bs] (optional), do_guidance, do_reconstruction
@@ -142,8 +144,9 @@ class Gaussian4DBatchRenderer:
                                  bool(batch.get("do_guidance", True)), bool(batch.get("do_reconstruction", True)))
         return {"comp_rgb": r["render"].permute(0, 2, 3, 1), "comp_depth": r["depth"].permute(0, 2, 3, 1),
                 "comp_mask": r["mask"].permute(0, 2, 3, 1), "viewspace_points": r["viewspace_points"],
-                "visibility_filter": [x > 0 for x in r["radii"]], "radii": list(r["radii"]), "means3D": list(r["means3D"]),
-                "scales": list(r["scales"]), "rotations": list(r["rotations"]), "opacities": [r["opacities"]] * bs}
+                "visibility_filter": list((r["radii"] > 0).unbind(0)), "radii": list(r["radii"].unbind(0)),
+                "means3D": list(r["means3D"]), "scales": list(r["scales"]), "rotations": list(r["rotations"]),
+                "opacities": [r["opacities"]] * bs}
 
 
 @register("diff-gaussian-rasterizer-advanced-4d")

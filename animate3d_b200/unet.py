@@ -134,6 +134,9 @@ class MVUNetMotionModel(torch.nn.Module):
         self.gemm_impl = L.IMPL_AUTO
         self.attn_impl = L.IMPL_AUTO
         self.launches = 0            # kernel launches issued by the last eager run (bench's gpu_launches claim)
+        self.collectives = 0         # view-sharded mode: K|V all-gathers issued by the last eager run and their payload
+        self.collective_bytes = 0
+        self.comm_enabled = True     # False = skip the all-gathers (timing only: measures the compute of the sharded forward)
         self.eval()
         self.requires_grad_(False)
 
@@ -266,6 +269,20 @@ class MVUNetMotionModel(torch.nn.Module):
         self._loaded.update(k for k in sd if k in plan)
         self._prepared = False
         return res
+
+    def share_packed_weights(self, other: "MVUNetMotionModel"):
+        """Use `other`'s packed fp16 operands (same geometry, same device) instead of packing a second copy -- e.g. a
+        view-sharded engine next to a whole-batch one in the same process (bench.py)."""
+        if not other._prepared:
+            other._prepare()
+        if other.cfg != self.cfg or other.device != self.device:
+            raise ValueError("share_packed_weights: geometry / device differ")
+        self.W, self._kv_off = other.W, other._kv_off
+        self._prepared = True
+        self._masters_dropped = True
+        for p_ in list(self.parameters()) + list(self.buffers()):
+            p_.data = torch.empty(0, device=p_.device, dtype=p_.dtype)
+        self._graphs.clear(); self._static.clear()
 
     def drop_reference_weights(self):
         """Free the fp32 master copies (6 GB for the released geometry) once the packed operands exist; `state_dict()` is then
@@ -513,19 +530,36 @@ class MVUNetMotionModel(torch.nn.Module):
         self.launches += 1
         ops.attention(q, k, v, out, ostr, heads=self.cfg.num_attention_heads, d=d, scale=d ** -0.5, impl=self.attn_impl, **kw)
 
-    def _gathered_views(self, ln, lin, n_q, M, lvl, hq, q_strides, kv_strides, hw, F, B, table, rb_div, rb_mod):
-        """View-parallel projection: the fused [q.. | k | v] projection is split by rows into a local query GEMM and a K|V
-        GEMM whose output is all-gathered over the view group; returns (q view, second q view, k view, v view)."""
+    def _kv_gather_start(self, ln, lin, n_q, M, lvl, table, rb_div, rb_mod):
+        """View-parallel projection, first half: the K|V rows of the fused [q.. | k | v] projection are computed FIRST and their
+        all-gather over the view group is started asynchronously (NCCL runs it on its own stream over NVLink); the caller keeps
+        issuing work that does not need the remote views (the query projection, the whole temporal branch of a motion module)
+        and calls `_kv_gather_finish` right before the cross-view attention.  Returns a token for `_kv_gather_finish`."""
         import torch.distributed as dist
         V = self.view_world
         n_kv = lin.n - n_q
-        qb = self._buf(f"qkv{lvl}", (M, n_q))
         kv_loc = self._buf(f"kvloc{lvl}", (M, n_kv))
         kv_all = self._buf(f"kvall{lvl}", (V, M, n_kv))
         rb = {} if table is None else {"rb_div": rb_div, "rb_mod": rb_mod}
-        self._gemm(ln, lin.rows(0, n_q), qb, M, rowbias=None if table is None else table[:, :n_q], **rb)
         self._gemm(ln, lin.rows(n_q, lin.n), kv_loc, M, rowbias=None if table is None else table[:, n_q:], **rb)
-        dist.all_gather_into_tensor(kv_all.view(-1), kv_loc.view(-1), group=self.view_group)
+        work = None
+        if self.comm_enabled:
+            work = dist.all_gather_into_tensor(kv_all.view(-1), kv_loc.view(-1), group=self.view_group, async_op=True)
+            self.collectives += 1
+            self.collective_bytes += kv_loc.numel() * 2 * (V - 1)
+        return work, kv_all, n_kv
+
+    def _q_project(self, ln, lin, n_q, M, lvl, table, rb_div, rb_mod):
+        qb = self._buf(f"qkv{lvl}", (M, n_q))
+        rb = {} if table is None else {"rb_div": rb_div, "rb_mod": rb_mod}
+        self._gemm(ln, lin.rows(0, n_q), qb, M, rowbias=None if table is None else table[:, :n_q], **rb)
+        return qb
+
+    def _kv_gather_finish(self, token, qb, n_q, hq, q_strides, kv_strides, hw, F, B):
+        work, kv_all, n_kv = token
+        if work is not None:
+            work.wait()            # the compute stream waits for the gathered K|V (no host sync)
+        V = self.view_world
         ext_q, ext_k = (hw, 1, F, B), (hw, V, F, B)
         vq = ops.view5(qb, 0, n_q, q_strides(n_q), ext_q)
         vq2 = ops.view5(qb, hq, n_q - hq, q_strides(n_q), ext_q) if n_q > hq else None
@@ -561,9 +595,12 @@ class MVUNetMotionModel(torch.nn.Module):
             vk = ops.view5(qkv, 2 * hq, nq - 2 * hq, st, ext)
             vv = ops.view5(qkv, 3 * hq, nq - 3 * hq, st, ext)
         else:
-            # views span ranks: local rows are (b f p) of ONE view; K|V of every view are all-gathered
-            vq, vqi, vk, vv = self._gathered_views(ln, t["qkv"], 2 * hq, M, lvl, hq, (lambda n_: (n_, F * hw * n_, hw * n_, F * hw * n_)),
-                                                   (lambda n_: (n_, M * n_, hw * n_, F * hw * n_)), hw, F, B, None, 0, 0)
+            # views span ranks: local rows are (b f p) of ONE view; K|V of every view are all-gathered while the two query
+            # projections run
+            tok_kv = self._kv_gather_start(ln, t["qkv"], 2 * hq, M, lvl, None, 0, 0)
+            qb = self._q_project(ln, t["qkv"], 2 * hq, M, lvl, None, 0, 0)
+            vq, vqi, vk, vv = self._kv_gather_finish(tok_kv, qb, 2 * hq, hq, (lambda n_: (n_, F * hw * n_, hw * n_, F * hw * n_)),
+                                                     (lambda n_: (n_, M * n_, hw * n_, F * hw * n_)), hw, F, B)
         o12 = self._buf(f"ao{lvl}", (M, 2 * c))                                  # [O1 | O2], rows of 2C
         ostr12 = tuple(2 * s_ for s_ in ostr)
         self._attn(vq, vk, vv, o12, ostr12, d)
@@ -609,12 +646,16 @@ class MVUNetMotionModel(torch.nn.Module):
         for a, lnk in (("attn1", "ln1"), ("attn2", "ln2")):
             p = m[a]
             self._ln(tok, m[lnk], ln, M, c)
+            ns = p["s_qkv"].n
+            if self.view_group is not None:
+                # spatial (cross-view) K|V first: their all-gather overlaps the query projection and the WHOLE temporal branch
+                tok_kv = self._kv_gather_start(ln, p["s_qkv"], hq, M, lvl, p["s_table"], F, hw)
+                qb = self._q_project(ln, p["s_qkv"], hq, M, lvl, p["s_table"], F, hw)
             # temporal branch: (x + pe_t) W == x W + table[f]
             self._gemm(ln, p["t_qkv"], tq, M, rowbias=p["t_table"], rb_div=1, rb_mod=F)
             self.launches += 1
             ops.temporal_attn(tq, st2, M // F, F, heads, d, d ** -0.5, ldo=2 * c, out_col_offset=c)
             # spatial (cross-view) branch: (x + pos2d) W == x W + table[p]
-            ns = p["s_qkv"].n
             if self.view_group is None:
                 sq = self._buf(f"qkv{lvl}", (M, ns))
                 self._gemm(ln, p["s_qkv"], sq, M, rowbias=p["s_table"], rb_div=F, rb_mod=hw)
@@ -624,8 +665,8 @@ class MVUNetMotionModel(torch.nn.Module):
                 vk = ops.view5(sq, hq, ns - hq, st, ext)
                 vv = ops.view5(sq, 2 * hq, ns - 2 * hq, st, ext)
             else:
-                vq, _, vk, vv = self._gathered_views(ln, p["s_qkv"], hq, M, lvl, hq, (lambda n_: (F * n_, hw * F * n_, n_, hw * F * n_)),
-                                                     (lambda n_: (F * n_, M * n_, n_, hw * F * n_)), hw, F, B, p["s_table"], F, hw)
+                vq, _, vk, vv = self._kv_gather_finish(tok_kv, qb, hq, hq, (lambda n_: (F * n_, hw * F * n_, n_, hw * F * n_)),
+                                                       (lambda n_: (F * n_, M * n_, n_, hw * F * n_)), hw, F, B)
             self._attn(vq, vk, vv, st2, (2 * F * c, 2 * hw * F * c, 2 * c, 2 * Nv * hw * F * c), d)
             # AlphaBlender of both branches' output projections + the block residual: one GEMM, K = 2C
             self._gemm(st2, p["out"], tok, M, R2=tok, ldr2=c)
@@ -795,7 +836,7 @@ class MVUNetMotionModel(torch.nn.Module):
         if graph is not None:
             graph.replay()
         else:
-            self.launches = 0
+            self.launches = self.collectives = self.collective_bytes = 0
             self._run(sig, st)
             self.launches_per_forward = self.launches
             st["calls"] += 1

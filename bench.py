@@ -17,7 +17,18 @@ JSON line keys beyond the base contract:
   cpu_baseline the oracle port (oracle/unet_oracle.py) on the host cores for a bounded sample, extrapolated by FLOPs
   e2e          the same step through pipeline.denoise_step_host with pinned HOST buffers (H2D of the step inputs + D2H of
                the updated latents inside the timed region)
---impl reference times the oracle port (the reference's diffusers CPU path is not installable here: SURVEY section 8c).
+  roofline_gemm  the worst short-K projection (HBM-bound: bytes / time against the measured copy bandwidth) and the best long-K
+               implicit-GEMM convolution (tensor-bound) of the step, timed alone
+  splat        the second half of the BASELINE metric: Mpix/s of the batched 4D-gaussian renderer at BASELINE configs[2]
+               (50k gaussians, 4 views x 16 timestamps = 64 cameras at 512^2), forward and forward+backward, with per-stage
+               times from CUDA events inside liba3d.so and the stage rooflines of SURVEY 8(d); for N > 1 the cameras are
+               sharded r::N and the deformation-field gradients all-reduced (one flat bucket)
+  view_sharded (N > 1) ONE prompt spread over the N ranks -- CFG branches over 2 ranks and / or the 4 views over 4 ranks with
+               the cross-view K|V all-gather over NCCL -- as a strong-scaling number next to the weak-scaling `value`, with the
+               exposed communication time (same forward with the collectives skipped)
+--impl reference times the oracle port (the reference's diffusers CPU path is not installable here: SURVEY section 8c) on a
+BOUNDED sample per step (one forward of 4 views x 1 frame: the real L = 4096 cross-view attention shape); `ms_per_step` is the
+measured time of that sample, `value` the steps/s extrapolated by FLOPs -- flagged `extrapolated` / `same_config: false`.
 """
 import argparse
 import json
@@ -112,23 +123,25 @@ def best_cpu_threads(sd):
 
 
 def cpu_oracle_sample(repeats=1):
-    """Time the oracle port on the plumbing config (BASELINE config 0: 1 view x 4 frames) and extrapolate by FLOPs."""
+    """Time the oracle port on a bounded sample (one forward of 4 views x 1 frame: cross-view attention at its real
+    L = 4096) and extrapolate by FLOPs."""
     import torch
     from animate3d_b200.flops import unet_forward_flops
     from animate3d_b200.unet_config import UNetConfig
     from oracle import unet_oracle as O
-    ocfg = O.UNetConfig(num_views=1, num_frames=4)
+    nv, nf = 4, 1
+    ocfg = O.UNetConfig(num_views=nv, num_frames=nf)
     torch.set_num_threads(min(16, os.cpu_count() or 1))   # never run the oracle (or build its weights) on all cores
     sd = O.make_state_dict(ocfg, 0)
     cores = best_cpu_threads(sd)
-    sample, text, camera, img = O.synthetic_inputs(ocfg, 1, 1, 4, 0)
+    sample, text, camera, img = O.synthetic_inputs(ocfg, 1, nv, nf, 0)
     times = []
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            O.unet_forward(sd, ocfg, sample, 500, text, camera, img, 1)
+            O.unet_forward(sd, ocfg, sample, 500, text, camera, img, nv)
             times.append(time.perf_counter() - t0)
-    fl = unet_forward_flops(UNetConfig(), 1, 1, 4)["total"]
+    fl = unet_forward_flops(UNetConfig(), 1, nv, nf)["total"]
     return times, fl, cores
 
 
@@ -140,28 +153,34 @@ def run_reference(args, rank, world):
     from oracle import unet_oracle as O
     from animate3d_b200.flops import unet_forward_flops
     from animate3d_b200.unet_config import UNetConfig
-    nf = 1 if os.environ.get("A3D_BENCH_TINY") else 4
-    ocfg = O.UNetConfig(num_views=1, num_frames=nf)
+    tiny = bool(os.environ.get("A3D_BENCH_TINY"))
+    nv, nf = (1, 1) if tiny else (4, 1)
+    ocfg = O.UNetConfig(num_views=nv, num_frames=nf)
     torch.set_num_threads(min(16, os.cpu_count() or 1))   # never run the oracle (or build its weights) on all cores
     sd = O.make_state_dict(ocfg, 0)
     cores = best_cpu_threads(sd)
-    sample, text, camera, img = O.synthetic_inputs(ocfg, 1, 1, nf, 0)
-    fl = unet_forward_flops(UNetConfig(), 1, 1, nf)["total"]
+    sample, text, camera, img = O.synthetic_inputs(ocfg, 1, nv, nf, 0)
+    fl = unet_forward_flops(UNetConfig(), 1, nv, nf)["total"]
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.unet_forward(sd, ocfg, sample, 500, text, camera, img, 1)
+            O.unet_forward(sd, ocfg, sample, 500, text, camera, img, nv)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.unet_forward(sd, ocfg, sample, 500, text, camera, img, 1)
+            O.unet_forward(sd, ocfg, sample, 500, text, camera, img, nv)
         dt = (time.perf_counter() - t0) / args.steps
     val = (fl / dt) / sf
-    sample_desc = (f"each step = one fp32 oracle forward of 1 view x {nf} frames x 32x32x4 ({fl / 1e12:.2f} TFLOP of the "
-                   f"{sf / 1e12:.2f} TFLOP CFG step); steps/s extrapolated by FLOPs")
+    factor = sf / fl
+    sample_desc = (f"each step = one fp32 oracle forward of {nv} view(s) x {nf} frame(s) x 32x32x4 ({fl / 1e12:.2f} TFLOP of the "
+                   f"{sf / 1e12:.2f} TFLOP CFG step, cross-view attention at its real L = {nv * 1024}); steps/s extrapolated by "
+                   f"FLOPs (x{factor:.1f}); ms_per_step is the measured time of the sample")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "extrapolated": True, "same_config": False,
         "config": {"workload": "MV-VDM CFG denoise step, 1 prompt x 2 CFG x 4 views x 16 frames x 32x32x4 latents",
+                   "sample": sample_desc, "sample_tflop": fl / 1e12, "step_tflop": sf / 1e12, "extrapolation_factor": factor,
+                   "full_step_evidence": "profiles/r02_cpu_oracle_full_forward.txt (one full 4-view x 16-frame branch forward timed on "
+                                         "the GPU box inside tests/test_unet_gpu.py)",
                    "note": "reference's diffusers CPU path is not installable here; oracle port (oracle/unet_oracle.py) timed"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,6 +231,220 @@ def time_attention_l0(torch, iters=10):
     ms = e0.elapsed_time(e1) / iters
     flops = B * NF * 4.0 * (NV * hw) ** 2 * c
     return ms, flops
+
+
+def _time_cuda(torch, fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gemm_rooflines(torch, peak_tf, peak_hbm):
+    """Two GEMM shapes of the step timed alone (operands >> L2 are re-read every launch at level 0):
+    worst short-K  : the merged attention output projection at level 0, M=131072 N=320 K=640 + residual  -> HBM-bound
+    best long-K    : ResnetBlock2D conv3x3 1280->1280 at level 2, implicit GEMM M=8192 N=1280 K=11520 -> tensor-bound."""
+    from animate3d_b200 import ops
+    out = {}
+    M, N, K = 131072, 320, 640
+    A = torch.randn(M, K, device="cuda").half()
+    B = (torch.randn(N, K, device="cuda") * 0.05).half()
+    R2 = torch.randn(M, N, device="cuda").half()
+    bias = torch.randn(N, device="cuda")
+    C_ = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    ms = _time_cuda(torch, lambda: ops.gemm(A, B, C_, M=M, N=N, K=K, bias=bias, R2=R2, ldr2=N))
+    nbytes = 2.0 * (M * K + N * K + 2 * M * N)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    out["short_k"] = {"shape": f"M={M} N={N} K={K} +bias +residual (to_out([O1|O2]) at level 0)", "bound": "hbm", "us": ms * 1e3,
+                      "bytes": nbytes, "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                      "tflops": 2.0 * M * N * K / (ms * 1e-3) / 1e12}
+    n_img, h, w, c = 128, 8, 8, 1280
+    M, N, K = n_img * h * w, 1280, 9 * c
+    A = torch.randn(M, c, device="cuda").half()
+    B = (torch.randn(N, K, device="cuda") * 0.02).half()
+    R2 = torch.randn(M, N, device="cuda").half()
+    C_ = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    bias2 = torch.zeros(N, device="cuda")
+    ms = _time_cuda(torch, lambda: ops.gemm(A, B, C_, M=M, N=N, K=K, conv=(n_img, h, w, c, 1), bias=bias2, R2=R2, ldr2=N))
+    tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+    out["long_k"] = {"shape": f"conv3x3 {c}->{N} on {n_img}x{h}x{w} (implicit GEMM M={M} N={N} K={K}) +residual", "bound": "tensor",
+                     "us": ms * 1e3, "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf}
+    return out
+
+
+def splat_bench(torch, rank, world, peak_hbm, sm_mhz, iters=5):
+    """BASELINE configs[2] geometry: 50k gaussians, 4 views x 16 timestamps at 512^2.  world > 1: rank r
+    renders cameras r::world, the deformation-field gradients are summed with one flat all-reduce per step."""
+    import ctypes as C
+    import torch.distributed as dist
+    from animate3d_b200 import _lib as L
+    from animate3d_b200.parallel import allreduce_gradients, shard_cameras
+    from animate3d_b200.renderer import make_renderer
+    from tools.splat_bench import cameras, synthetic_model
+    P, H, W = 50000, 512, 512
+    lib = L.load()
+    model = synthetic_model(P)
+    rend = make_renderer(model)
+    c2w, fovy, ts = cameras()
+    full = {"c2w": c2w, "fovy": fovy, "width": W, "height": H, "timestamps": ts, "do_guidance": True, "do_reconstruction": True}
+    batch = shard_cameras(full, rank, world) if world > 1 else full
+    ncam_total, ncam = int(c2w.shape[0]), int(batch["c2w"].shape[0])
+    target = torch.rand(ncam, H, W, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def fwd():
+        return rend.batch_forward(batch)
+
+    def fwd_bwd():
+        for p_ in params:
+            p_.grad = None
+        out = rend.batch_forward(batch)
+        (0.5 * ((out["comp_rgb"] - target) ** 2).sum()).backward()
+        allreduce_gradients(params, world)
+
+    res = {}
+    for name, fn in (("fwd", fwd), ("fwd_bwd", fwd_bwd)):
+        fn(); fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = _time_cuda(torch, fn, iters=iters, warm=0)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        res[name] = ms
+    # one instrumented fwd+bwd on this rank: per-stage times from events inside liba3d.so
+    L.check(lib.a3d_debug_raster_timing(1))
+    fwd_bwd()
+    stage = (C.c_float * 8)()
+    L.check(lib.a3d_debug_raster_stage_ms(stage))
+    L.check(lib.a3d_debug_raster_timing(0))
+    st = {k: float(stage[i]) for i, k in enumerate(("preprocess", "scan_duplicate", "radix_sort", "ranges", "render_fwd",
+                                                    "render_bwd", "preprocess_bwd"))}
+    with torch.no_grad():
+        out = rend.batch_forward(batch)
+        radii = torch.stack(out["radii"])
+    from animate3d_b200 import rasterizer as RZ
+    pairs = int(RZ.last_num_rendered)                             # (tile, gaussian) pairs of this rank's cameras
+    tiles = (H // 16) * (W // 16)
+    passes = -(-(32 + max(1, (ncam * tiles).bit_length())) // 8)
+    # SURVEY 8(d) algorithmic bytes: preprocess 44 + 12 read, 72 written per (camera, gaussian); binning 12 B per pair written
+    # once + 2 x 12 B per pair per radix pass; render 44 B per pair + 28 B per pixel
+    b_pre = ncam * P * (44 + 12 + 72.0)
+    b_bin = pairs * 12.0 + passes * 2 * 12.0 * pairs
+    t_bin = (st["scan_duplicate"] + st["radix_sort"] + st["ranges"]) * 1e-3
+    evals = float(pairs) * 256.0                                   # pixel-gaussian evaluations (upper bound: early exit at T < 1e-4)
+    mufu_evals_s = 148 * 16 * sm_mhz * 1e6                          # one ex2 per evaluation, 16 per clock per SM
+    out = {"config": {"gaussians": P, "cameras": ncam_total, "cameras_per_rank": ncam, "H": H, "W": W,
+                      "scene": "SURVEY 8(d) config 3 (seeded synthetic), k-planes + 3 MLPs deformation per timestamp",
+                      "parallelism": "single GPU" if world == 1 else f"cameras r::{world}, 1 flat all-reduce of the deformation-field gradients"},
+           "fwd_mpix_s": ncam_total * H * W / res["fwd"] / 1e3, "fwd_bwd_mpix_s": ncam_total * H * W / res["fwd_bwd"] / 1e3,
+           "fwd_ms": res["fwd"], "fwd_bwd_ms": res["fwd_bwd"], "pairs_per_rank": pairs, "radix_passes": passes, "stages_ms": st,
+           "roofline": {
+               "preprocess": {"bound": "hbm", "bytes": b_pre, "achieved": b_pre / (st["preprocess"] * 1e-3) / 1e9 if st["preprocess"] else None,
+                              "peak": peak_hbm, "unit": "GB/s"},
+               "binning": {"bound": "hbm", "bytes": b_bin, "achieved": b_bin / t_bin / 1e9 if t_bin else None, "peak": peak_hbm,
+                           "unit": "GB/s"},
+               "render_fwd": {"bound": "xu (one ex2 per pixel-gaussian evaluation)", "evals": evals,
+                              "achieved": evals / (st["render_fwd"] * 1e-3) / 1e9 if st["render_fwd"] else None,
+                              "peak": mufu_evals_s / 1e9, "unit": "G eval/s"}}}
+    for v in out["roofline"].values():
+        if v.get("achieved"):
+            v["frac"] = v["achieved"] / v["peak"]
+    return out
+
+
+def view_sharded_bench(torch, args, rank, world, local_rank, base_model, timesteps):
+    """ONE prompt over all ranks (SURVEY 8e / BASELINE configs[3]): world 2 = the two CFG branches; world 4 = the 4 views (K|V
+    all-gather per cross-view attention); world 8 = both.  Returns steps/s of that single prompt, the exposed communication
+    (same sharded step with the all-gathers skipped) and the collective volume."""
+    import torch.distributed as dist
+    from animate3d_b200.pipeline import AnimateDiffMVI2VPipeline, get_camera
+    from animate3d_b200.scheduler import DDIMScheduler
+    from animate3d_b200.unet import MVUNetMotionModel
+    if world not in (2, 4, 8):
+        return None
+    cfg_world = 2 if world in (2, 8) else 1
+    view_world = 4 if world in (4, 8) else 1
+    cfg_idx, view_idx = rank // view_world, rank % view_world
+    view_group = cfg_group = None
+    for c in range(cfg_world):           # every rank creates every group, in the same order
+        g = dist.new_group([c * view_world + v for v in range(view_world)])
+        if c == cfg_idx and view_world > 1:
+            view_group = g
+    for v in range(view_world):
+        g = dist.new_group([c * view_world + v for c in range(cfg_world)])
+        if v == view_idx and cfg_world > 1:
+            cfg_group = g
+    dev = torch.device("cuda", local_rank)
+    cfg = base_model.cfg
+    model = MVUNetMotionModel(cfg, device=dev, view_group=view_group)
+    model.share_packed_weights(base_model)
+    sched = DDIMScheduler()
+    sched.set_timesteps(25)
+    pipe = AnimateDiffMVI2VPipeline(unet=model, scheduler=sched)
+    g = torch.Generator(device=dev).manual_seed(4242)               # the SAME prompt on every rank
+    lat = torch.randn(NV, 4, NF, LAT, LAT, device=dev, generator=g)
+    pe = torch.randn(2 * NV, 77, cfg.cross_attention_dim, device=dev, generator=g)
+    ie = torch.randn(2 * NV, cfg.ip_image_embed_dim, device=dev, generator=g)
+    ie[:NV] = 0
+    cam = get_camera(NV).to(dev)
+    vs = slice(view_idx, view_idx + 1) if view_world > 1 else slice(0, NV)
+    nloc = 1 if view_world > 1 else NV
+    lat_loc = lat[vs].contiguous()
+    first_loc = lat_loc[:, :, :1].clone()
+    pick = lambda x: x.reshape(2, NV, *x.shape[1:])[:, vs]            # (branch, view, ...)
+    if cfg_world > 1:
+        pe_l, ie_l, cam_l = pick(pe)[cfg_idx], pick(ie)[cfg_idx], cam[vs]
+    else:
+        pe_l, ie_l = pick(pe).reshape(2 * nloc, *pe.shape[1:]), pick(ie).reshape(2 * nloc, *ie.shape[1:])
+        cam_l = torch.cat([cam[vs], cam[vs]])
+
+    def run(n, x):
+        for i in range(n):
+            pipe.denoise_step_sharded(x, timesteps[i % len(timesteps)], pe_l, cam_l, ie_l, first_loc, 7.5, cfg_group=cfg_group,
+                                      num_views_local=nloc)
+
+    def timed(comm):
+        model.comm_enabled = comm
+        model._graphs.clear()
+        for st_ in model._static.values():
+            st_["calls"] = 0
+        x = lat_loc.clone()
+        run(3, x)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(args.steps, x)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / args.steps, x
+
+    ms, x = timed(True)
+    finite = bool(torch.isfinite(x).all())
+    ncoll, nbytes = model.collectives, model.collective_bytes
+    ms_nocomm = None
+    if view_world > 1:
+        ms_nocomm, _ = timed(False)
+        model.comm_enabled = True
+    return {"value": 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "scaling": "strong",
+            "mode": f"1 prompt over {world} ranks = {cfg_world} CFG rank(s) x {view_world} view rank(s)",
+            "collectives_per_forward": ncoll, "kv_bytes_received_per_rank_per_forward": nbytes,
+            "cfg_allgather_bytes_per_step": (2 * nloc * 4 * NF * LAT * LAT * 4) if cfg_world > 1 else 0,
+            "ms_per_step_collectives_skipped": ms_nocomm,
+            "exposed_comm_ms_per_step": (ms - ms_nocomm) if ms_nocomm is not None else None,
+            "overlap": "K|V all-gather issued async right after the K|V projection; query projection and the temporal branch run under it",
+            "cuda_graph": bool(model._graphs), "finite": finite}
 
 
 def run_native(args, rank, world, local_rank):
@@ -296,25 +529,30 @@ def run_native(args, rank, world, local_rank):
     h2d = sum(x.numel() * x.element_size() for x in (lat_h, pe_h, cam_h, ie_h, ff_h))
     d2h = out_h.numel() * out_h.element_size()
 
+    peak_tf, peak_hbm, peak_src = peaks()
+    sharded = view_sharded_bench(torch, args, rank, world, local_rank, model, timesteps) if world > 1 else None
+    del lat_h, pe_h, cam_h, ie_h, ff_h, out_h
+    splat = splat_bench(torch, rank, world, peak_hbm, float((clocks or {}).get("sm_mhz") or 1965.0))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     sf = step_flops()
-    peak_tf, peak_hbm, peak_src = peaks()
     att_ms, att_flops = time_attention_l0(torch)
     att_tf = att_flops / (att_ms * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("attn_l0_dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get("attn_l0_dram_bytes_per_launch")     # ncu dram__bytes_read+write per launch (r01 capture)
+    gemm_rf = gemm_rooflines(torch, peak_tf, peak_hbm)
     cpu = None
     if world == 1:
         times, fl, cores = cpu_oracle_sample(1)
         cpu_val = (fl / min(times)) / sf
         cpu = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"one fp32 oracle forward of 1 view x 4 frames ({fl / 1e12:.2f} TFLOP, {min(times):.1f} s) extrapolated by "
-                         f"FLOPs to the {sf / 1e12:.2f} TFLOP CFG step"}
+               "extrapolated": True,
+               "sample": f"one fp32 oracle forward of 4 views x 1 frame ({fl / 1e12:.2f} TFLOP, {min(times):.1f} s; cross-view "
+                         f"attention at L = 4096) extrapolated by FLOPs (x{sf / fl:.1f}) to the {sf / 1e12:.2f} TFLOP CFG step"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
@@ -328,7 +566,13 @@ def run_native(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "a3d_attention head_dim 40 (fused cross-view attention, L=4096, 32 batches x 8 heads)",
                      "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf, "traffic": traffic,
                      "ms_per_launch": att_ms, "flop_per_launch": att_flops, "peak_source": peak_src,
-                     "mufu": mufu_note(att_flops, att_ms, clocks)},
+                     "mufu": mufu_note(att_flops, att_ms, clocks),
+                     "note": "0.6x of the tensor peak is not reachable at head_dim 40: every score needs one exponential; the XU "
+                             "pipe (MUFU.EX2 8 cycles / warp instruction + F2FP 4) floors the kernel at `mufu.floor_ms` "
+                             "(tensor-only bound would be 0.31 ms); logits here are randn, the in-step kernel time agrees within 2 %"},
+        "roofline_gemm": gemm_rf,
+        "splat": splat,
+        "view_sharded": sharded,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": (model.launches_per_forward + 1) * args.steps,

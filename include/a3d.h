@@ -264,11 +264,20 @@ int a3d_arap(const float* nodes, int Nt, int Nv, const int32_t* nbr, int K, cons
              float* err, float* grad, void* stream);
 
 /* debug hook: a device uint64 counter the tcgen05 attention kernels bump once per (warp, key step) that takes the
-   lazy-rescale branch of the single-pass softmax (NULL = off; tests use it to prove adversarial inputs reach that branch) */
+   lazy-rescale branch of the single-pass softmax (NULL = off; tests use it to prove adversarial inputs reach that branch).
+   The buffer must hold 8 + 4*32*8 uint64: words 8.. receive a clock64 timeline of four softmax warps of CTA (0,0,0) of the
+   head-dim-40 kernel (tools/attn_timeline.py) */
 int a3d_debug_set_attn_trace(void* device_counter_u64);
-/* tuning hook: number (0..3) of every 4 score pairs whose exponential the head-dim-40 attention kernel evaluates on the FMA
-   pipe (half2 polynomial) instead of MUFU.EX2; see csrc/a3d_attn.cu "softmax arithmetic of the v5 kernel" */
-int a3d_debug_set_attn_poly(int pairs_of_four);
+/* tuning hook of the head-dim-40 attention kernel: bits 0-3 = number (0..3) of every 4 score pairs whose exponential runs on
+   the FMA pipe (half2 polynomial) instead of MUFU.EX2; bits 4-7 = how many softmax warps of an SM sub-partition may be in their
+   exponential phase at once (XU turn-taking; 0 = unconstrained).  See csrc/a3d_attn.cu. */
+int a3d_debug_set_attn_poly(int poly_and_concurrency);
+/* measurement hooks of the rasterizer (bench.py's splat roofline): with timing enabled every forward / backward records CUDA
+   events at its stage boundaries; a3d_debug_raster_stage_ms returns the milliseconds of the last forward's stages
+   [0] preprocess [1] scan + counts + duplicate [2] radix sort [3] tile ranges [4] render and the last backward's [5] render
+   backward [6] preprocess backward ([7] unused) */
+int a3d_debug_raster_timing(int enable);
+int a3d_debug_raster_stage_ms(float* out_host8);
 /* same for the tcgen05 GEMM: per-tile timestamps of CTA 0 (epilogue warp 0 and the MMA-issuing thread) */
 int a3d_debug_set_gemm_trace(void* device_buffer_1024_int64);
 

@@ -60,3 +60,45 @@ def test_bench_reference_arm_under_torchrun_rank0_only(tmp_path):
     import json
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+CAM_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["A3D_ROOT"])
+from animate3d_b200.parallel import shard_cameras, allreduce_gradients, gather_renders, scatter_render_grads
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+bs = 7
+batch = {"c2w": torch.arange(bs * 16, dtype=torch.float32).reshape(bs, 4, 4), "fovy": torch.arange(bs, dtype=torch.float32),
+         "timestamps": torch.linspace(-1, 1, bs), "width": 8, "height": 8, "do_guidance": True}
+sub = shard_cameras(batch, rank, world)
+assert sub["camera_index"].tolist() == list(range(rank, bs, world)) and sub["width"] == 8
+assert torch.equal(sub["fovy"], batch["fovy"][rank::world]) and torch.equal(sub["c2w"], batch["c2w"][rank::world])
+# a toy "renderer": image_i = w * fovy_i ; loss = sum_i image_i * (i + 1)  ->  dL/dw = sum_i fovy_i * (i + 1)
+w = torch.nn.Parameter(torch.tensor([2.0, -1.0]))
+unused = torch.nn.Parameter(torch.zeros(3))
+local = (w[None, :] * sub["fovy"][:, None])                                   # [n_local, 2]
+full = gather_renders(local, rank, world, bs)
+assert torch.allclose(full, torch.tensor([2.0, -1.0])[None] * batch["fovy"][:, None])
+full_grad = (torch.arange(bs, dtype=torch.float32) + 1)[:, None].expand(bs, 2).contiguous()
+local.backward(scatter_render_grads(full_grad, rank, world))
+nbytes = allreduce_gradients([w, unused], world)
+want = (batch["fovy"] * (torch.arange(bs) + 1)).sum()
+assert nbytes == 5 * 4 and torch.allclose(w.grad, torch.stack([want, want])), (w.grad, want)
+assert unused.grad is not None and unused.grad.abs().sum() == 0
+dist.barrier()
+if rank == 0:
+    print("CAM_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_world2_camera_sharding_and_grad_allreduce(tmp_path):
+    """Rasterizer sharding of SURVEY 8e: cameras r::N per rank, forward all-gather of the renders, ONE flat all-reduce of
+    the deformation-field gradients -- equals the single-process gradient."""
+    script = tmp_path / "cam_worker.py"
+    script.write_text(CAM_WORKER)
+    env = dict(os.environ, A3D_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29535", str(script)], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "CAM_OK" in r.stdout, r.stdout + r.stderr

@@ -46,10 +46,10 @@ def accuracy(kind):
     return (e.norm() / ref.norm()).item(), (e.abs().max() / ref.abs().max()).item()
 
 
-for poly in (0, 1, 2, 3):
-    L.check(lib.a3d_debug_set_attn_poly(poly))
+for conc, poly, early in ((0, 0, 0), (0, 0, 1), (3, 0, 1), (0, 1, 1)):
+    L.check(lib.a3d_debug_set_attn_poly(poly | (conc << 4) | (early << 8)))
     r1, m1 = accuracy("randn")
     r2, m2 = accuracy("wide")
-    print(f"poly pairs {poly}/4: randn rel-l2 {r1:.2e} max {m1:.2e} | wide rel-l2 {r2:.2e} max {m2:.2e}")
-    kb.attn_case(f"l0 cross-view poly={poly}", 2, 4, 16, 1024, 40)
-L.check(lib.a3d_debug_set_attn_poly(2))
+    print(f"early tests {early} xu concurrency {conc} poly pairs {poly}/4: randn rel-l2 {r1:.2e} max {m1:.2e} | wide rel-l2 {r2:.2e} max {m2:.2e}")
+    kb.attn_case(f"l0 cross-view early={early} conc={conc} poly={poly}", 2, 4, 16, 1024, 40)
+L.check(lib.a3d_debug_set_attn_poly(1 << 8))

@@ -73,5 +73,27 @@ def run(P=50000, H=512, W=512, iters=5):
     return res
 
 
+def profile_one():
+    """One forward+backward between cudaProfilerStart/Stop (ncu --profile-from-start off): the launch list of a whole SDS-style
+    render step -- deformation field, rasterizer stages, loss, every autograd kernel in between."""
+    from animate3d_b200.renderer import make_renderer
+    model = synthetic_model(50000)
+    r = make_renderer(model)
+    c2w, fovy, ts = cameras()
+    batch = {"c2w": c2w, "fovy": fovy, "width": 512, "height": 512, "timestamps": ts, "do_guidance": True, "do_reconstruction": True}
+    target = torch.rand(c2w.shape[0], 512, 512, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    for it in range(2):
+        if it == 1:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+        out = r.batch_forward(batch)
+        (0.5 * ((out["comp_rgb"] - target) ** 2).sum()).backward()
+        torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
 if __name__ == "__main__":
-    print(json.dumps(run()))
+    if "--profile" in sys.argv:
+        profile_one()
+    else:
+        print(json.dumps(run()))
