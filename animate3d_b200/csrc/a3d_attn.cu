@@ -31,7 +31,6 @@ struct AttnDev {
   int accumulate;
   float out_scale;
   int early_test;            // head-dim-40 kernel: non-blocking barrier tests one step ahead (see the step loop)
-  int xu_conc;               // head-dim-40 kernel: warps of an SM sub-partition allowed in their exponential phase at once (0 = free)
   unsigned long long* dbg;   // debug (null in production): dbg[0] counts (warp, step) pairs that took the lazy-rescale branch;
                              // dbg[8 + (w*32 + j)*8 + k]: clock64 timeline of 4 softmax warps of CTA (0,0,0) (head-dim-40 kernel)
 };
@@ -663,17 +662,15 @@ attn4_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 // ---------------------------------------------------------------------------------------------------------------
 // softmax arithmetic of the v5 kernel
 //   * the exponent offset carries a fixed bias: P' = 2^(y + kPBias) with y = s*scale*log2e - stabiliser.  The bias cancels in
-//     O / rowsum (the row sum is the ones column of V, accumulated from the same P'); it moves the fp16 flush-to-zero point from
-//     2^-14 to 2^-24 of the stabiliser, so the polynomial path below and the MUFU+F2FP path drop the same (negligible) tail.
-//     Head-room: y <= kRescale5 (stale stabiliser), so P' <= 2^(4+10) < 65504.
-//   * MUFU path  : ex2.approx(y + bias) per score, cvt.rn.f16x2 per pair            -> 20 XU-pipe cycles per pair
-//   * poly path  : 2^y on the FMA pipe in half2 arithmetic, Cody-Waite style:        ->  4 XU-pipe cycles per pair (the cvt)
-//       h = cvt.f16x2(y); h = max(h, -25); t = h + 1536 (rounds to integer: fp16 ulp is 1 there); n = t - 1536; f = h - n in
-//       [-0.5, 0.5]; p = c0 + f(c1 + f(c2 + f c3)) (minimax for 2^f, 6.9e-4 max / 2.5e-4 rms relative in fp16);
-//       2^(n + bias) is built as fp16 bits ((n + 25) << 10) from the low 6 mantissa bits of t and multiplied in (exact).
-//     Precision of y in fp16 matters only near the stabiliser (|y| < 4: ulp <= 2^-9 -> 7e-4 relative in 2^y); far below it the
-//     weights are small.  MUFU.EX2 is 8 cycles per warp instruction and shares its pipe with F2FP (profiles/
-//     r01_pipes_ubench.txt): moving POLY of every 4 pairs off it lowers the pipe floor from 20 to 20 - 4*POLY cycles per pair.
+//     O / rowsum (the row sum is the ones column of V, accumulated from the same P'); it moves the fp16 flush-to-zero point of
+//     cvt.rn.f16x2 from 2^-14 to 2^-24 of the stabiliser.  Head-room: y <= kRescale5 (stale stabiliser), P' <= 2^14 < 65504.
+//   * y for a score pair comes from one packed fma.rn.f32x2; ex2.approx per score, cvt.rn.f16x2 per pair: 20 XU-pipe cycles per
+//     pair (MUFU.EX2 8 cycles per warp instruction, F2FP 4, same pipe: profiles/r01_pipes_ubench.txt) -- the kernel's floor.
+//   Measured and NOT kept (profiles/r02_attn_experiments.txt, code in git history at the commit named there): a half2
+//   Cody-Waite polynomial 2^y on the FMA pipe for 1-3 of every 4 pairs (correct to 3.6e-4 rel-l2, but the softmax warps are
+//   issue-bound once the XU pipe is relieved: 1.85 -> 1.91 / 1.98 / 2.08 ms); XU turn-taking tickets between the warps of an
+//   SM sub-partition (a single warp reaches only ~45 % of the pipe: 1.97 -> 3.37 / 2.22 / 2.14 ms for 1 / 2 / 3 warps at a
+//   time); a software-pipelined step loop with split TMEM loads (2.13 -> 2.23 ms).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr float kPBias = 10.0f;
 constexpr float kRescale5 = 4.0f;
@@ -693,21 +690,6 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
-}
-__device__ __forceinline__ uint32_t exp2_h2(uint32_t h) {   // h: two fp16 exponents <= ~5; returns fp16x2 2^(h + kPBias)
-  uint32_t t, n, f, pl, e, r;
-  asm("max.f16x2 %0, %1, %2;" : "=r"(h) : "r"(h), "r"(0xCE40CE40u));            // -25.0: everything below flushes to 0
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(t) : "r"(h), "r"(0x66006600u));          // + 1536.0
-  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(n) : "r"(t), "r"(0x66006600u));
-  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(f) : "r"(h), "r"(n));
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(pl) : "r"(0x2B112B11u), "r"(f), "r"(0x33C433C4u));   // c3 f + c2
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(pl) : "r"(pl), "r"(f), "r"(0x398C398Cu));
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(pl) : "r"(pl), "r"(f), "r"(0x3C003C00u));
-  // exponent field (n + 25 + ... ) : t = 0x6600 + n per half -> low 6 bits = n mod 64; + 25 -> 0 .. 29 for n in [-25, 4]
-  asm("mad.lo.u32 %0, %1, 1024, %2;" : "=r"(e) : "r"(t), "r"(0x64006400u));
-  e &= 0x7C007C00u;
-  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(pl), "r"(e));
-  return r;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -745,7 +727,7 @@ struct Attn5Cfg {
 };
 
 // POLY: how many of the 4 fp16x2 pairs of every 8-key chunk take exp2 on the FMA pipe (exp2_fma) instead of MUFU.
-template <int D, int POLY>
+template <int D>
 __global__ void __launch_bounds__(640, 1)
 attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV) {
@@ -770,7 +752,6 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
   uint64_t* pv_done = p_full + 8;              // [2][2][2]
   uint64_t* o_full = pv_done + 8;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-  uint32_t* xu_turn = tmem_slot + 4;           // [4 sub-partitions] exponential phases completed (XU turn-taking)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -787,7 +768,6 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
-  if (threadIdx.x < 4) xu_turn[threadIdx.x] = 0;
   if (warp == 18 && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
@@ -933,8 +913,6 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       uint32_t p_off[4];      // this thread's four 16-byte P chunks of a step (128B-swizzled row r, chunks 4h .. 4h+3)
 #pragma unroll
       for (int c16 = 0; c16 < 4; ++c16) p_off[c16] = sw128_offset(r, 4 * h + c16);
-      const int nk = has1 ? 4 : 2, kslot = has1 ? 2 * g + h : h;          // warps of this sub-partition in the XU rotation
-      const uint32_t turn_addr = smem_u32(xu_turn + quad);
       const uint64_t sc2 = pack2(p.scale_log2, p.scale_log2);
       const int oc0 = h ? Cfg::kOChunks0 : 0, oc1 = h ? Cfg::kOChunks : Cfg::kOChunks0;
       // "is S(j+1) there" / "are the P columns of step j+1 free" are TESTED (non-blocking) while step j's exponentials run and
@@ -977,15 +955,6 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           s_ok = j + 1 < n && mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1);
           p_ok = j + 1 < 2 || mbar_test(&my_pv_done[(j + 1) & 1], ((j - 1) >> 1) & 1);
         }
-        // XU turn-taking: the softmax warps of an SM sub-partition share ONE MUFU pipe.  Left alone they fall into lockstep
-        // (processor sharing makes them finish their exponentials together) and then sit in barrier / fence latency together
-        // while the pipe idles -- profiles/r02_attn_timeline.txt.  A per-sub-partition ticket makes them take the pipe in a
-        // fixed rotation, at most `p.xu_conc` warps at a time, so one warp's publish / wait phase overlaps the others'
-        // exponentials.
-        if (p.xu_conc > 0) {
-          const uint32_t need = (uint32_t)(nk * j + kslot);
-          while (ld_volatile_shared(turn_addr) + (uint32_t)p.xu_conc <= need) {}
-        }
         if (tr) trow[2] = clock64();
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
@@ -993,7 +962,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           // the same loop.  Only when a row's new max exceeds the stabiliser by more than kRescale5 (P could overflow
           // fp16) is the step redone with the updated stabiliser -- after the first few steps that never happens.
           float mx0 = -INFINITY, mx1 = -INFINITY;
-          const uint64_t nm_mufu = pack2(kPBias - m_run, kPBias - m_run), nm_poly = pack2(-m_run, -m_run);
+          const uint64_t nm2 = pack2(kPBias - m_run, kPBias - m_run);
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
             uint4 q;
@@ -1003,11 +972,9 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
               const int i = c16 * 8 + 2 * t;
               const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]);
               if (t & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
-              // which pairs of an 8-key chunk take the FMA-pipe exponential: POLY 1 -> pair 1; 2 -> pairs 1, 3; 3 -> 0, 1, 3
-              const bool poly = POLY == 1 ? (t == 1) : POLY == 2 ? (t & 1) : POLY == 3 ? (t != 2) : POLY == 4;
               float y0, y1;
-              unpack2(ffma2(pack2u(s[i], s[i + 1]), sc2, poly ? nm_poly : nm_mufu), y0, y1);
-              qw[t] = poly ? exp2_h2(pack_f16x2(y0, y1)) : pack_f16x2(ex2_approx(y0), ex2_approx(y1));
+              unpack2(ffma2(pack2u(s[i], s[i + 1]), sc2, nm2), y0, y1);
+              qw[t] = pack_f16x2(ex2_approx(y0), ex2_approx(y1));
             }
             st_shared_v4(sPg + p_off[c16], q);
           }
@@ -1031,10 +998,6 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           }
           tmem_wait_st();
           m_run = m_up;
-        }
-        if (p.xu_conc > 0) {
-          __syncwarp();
-          if (lane == 0) red_add_shared(turn_addr, 1u);
         }
         if (tr) trow[3] = clock64();
         fence_proxy_async_smem();
@@ -1477,7 +1440,7 @@ static int tile_geom_k64(const a3d_view5& v, int* box1, int* box2, int* t1, int*
   return 0;
 }
 
-template <int D, int POLY>
+template <int D>
 static int launch_attn5(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
   using Cfg = Attn5Cfg<D>;
   int kb1, kb2, kt1, ktiles, klast;
@@ -1489,11 +1452,11 @@ static int launch_attn5(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
   if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
   static bool attr_set = false;
   if (!attr_set) {
-    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn5_tc_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn5_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   grid.x = (grid.x + 1) / 2;
-  attn5_tc_kernel<D, POLY><<<grid, 640, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  attn5_tc_kernel<D><<<grid, 640, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
@@ -1520,8 +1483,6 @@ static int launch_attn4(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
 }
 
 static unsigned long long* g_attn_dbg = nullptr;
-static int g_attn_poly = 0;   // pairs (of every 4) whose exponential runs on the FMA pipe in the head-dim-40 kernel
-static int g_attn_xu_conc = 0;
 static int g_attn_early = 1;
 
 }  // namespace a3d
@@ -1617,7 +1578,6 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   dev.accumulate = a->accumulate;
   dev.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
   dev.dbg = g_attn_dbg;
-  dev.xu_conc = g_attn_xu_conc;
   dev.early_test = g_attn_early;
   if ((a->os1 | a->os2 | a->os3 | a->os4) % 8 || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
@@ -1632,12 +1592,7 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   if (batches > 65535 || a->heads > 65535) return fail(A3D_EINVAL, "a3d_attention: grid too large");
   switch (d) {
     case 40:
-      switch (g_attn_poly) {
-        case 0: return launch_attn5<40, 0>(dev, a, mq, grid, st);
-        case 1: return launch_attn5<40, 1>(dev, a, mq, grid, st);
-        case 3: return launch_attn5<40, 3>(dev, a, mq, grid, st);
-        default: return launch_attn5<40, 2>(dev, a, mq, grid, st);
-      }
+      return launch_attn5<40>(dev, a, mq, grid, st);
     case 80:
       return launch_attn4<80, 0>(dev, a, mq, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
@@ -1651,14 +1606,8 @@ extern "C" int a3d_debug_set_attn_trace(void* device_counter_u64) {   // buffer 
   return A3D_OK;
 }
 
-// tuning hook (tools/attn_variants.py): how many of every 4 score pairs of the head-dim-40 kernel take the FMA-pipe
-// exponential (0 = all MUFU ... 3); the product default is set where g_attn_poly is defined
-extern "C" int a3d_debug_set_attn_poly(int pairs_of_four) {
-  // bits 0-3: polynomial pairs (0..3); bits 4-7: XU turn-taking concurrency (0 = off, 1..4)
-  const int poly = pairs_of_four & 15, conc = (pairs_of_four >> 4) & 15;
-  if (poly > 3 || conc > 4) return a3d::fail(A3D_EINVAL, "a3d_debug_set_attn_poly: poly 0..3, concurrency 0..4");
-  a3d::g_attn_poly = poly;
-  a3d::g_attn_xu_conc = conc;
-  a3d::g_attn_early = (pairs_of_four >> 8) & 1;
+// tuning hook (tools/attn_timeline.py): 0 switches the one-step-ahead non-blocking barrier tests of the head-dim-40 kernel off
+extern "C" int a3d_debug_set_attn_poly(int early_tests) {
+  a3d::g_attn_early = early_tests ? 1 : 0;
   return A3D_OK;
 }

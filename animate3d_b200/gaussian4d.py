@@ -47,6 +47,17 @@ def _args(xyz, scaling, rotation, times, planes, w1s, w2s, deform_scale, gplanes
     return a
 
 
+def _plane_grad_scratch(plane: torch.Tensor) -> torch.Tensor:
+    """Channel-last accumulation buffer [H, W, C] for the gradient of a [1, C, H, W] plane (a3d_deform_backward writes the C
+    channels of a texel as contiguous vector reductions)."""
+    _, c, h, w = plane.shape
+    return torch.zeros(h, w, c, device=plane.device, dtype=torch.float32)
+
+
+def _plane_grad_out(scratch: torch.Tensor, plane: torch.Tensor) -> torch.Tensor:
+    return scratch.permute(2, 0, 1).reshape(plane.shape).contiguous()
+
+
 class _FeatMean(torch.autograd.Function):
     """hidden_feats.mean(0) of every frame: [T, 32]; backward folds d/d mean into the plane gradients."""
 
@@ -70,14 +81,14 @@ class _FeatMean(torch.autograd.Function):
         n_planes = ctx.n_planes
         xyz, scaling, rotation, times, *rest = ctx.saved_tensors
         planes, w1s, w2s = rest[:n_planes], rest[n_planes:n_planes + 3], rest[n_planes + 3:]
-        gp = [torch.zeros_like(p) for p in planes]
+        gp = [_plane_grad_scratch(p) for p in planes]
         g1 = [torch.zeros_like(w) for w in w1s]
         g2 = [torch.zeros_like(w) for w in w2s]
         g_mean = g_mean.contiguous().float()
         a = _args(xyz, scaling, rotation, times, planes, w1s, w2s, True, gp, g1, g2)
         a.grad_featmean = g_mean.data_ptr()
         L.check(lib.a3d_deform_backward(C.byref(a), None, None, None, L.stream_ptr()))
-        return (None, None, None, None, None, *gp, None, None, None, None, None, None)
+        return (None, None, None, None, None, *[_plane_grad_out(g, p) for g, p in zip(gp, planes)], None, None, None, None, None, None)
 
 
 class _Deform(torch.autograd.Function):
@@ -111,7 +122,7 @@ class _Deform(torch.autograd.Function):
         deform_scale, n_planes = ctx.meta
         xyz, scaling, rotation, times, *rest = ctx.saved_tensors
         planes, w1s, w2s = rest[:n_planes], rest[n_planes:n_planes + 3], rest[n_planes + 3:]
-        gp = [torch.zeros_like(p) for p in planes]
+        gp = [_plane_grad_scratch(p) for p in planes]
         g1 = [torch.zeros_like(w) for w in w1s]
         g2 = [torch.zeros_like(w) for w in w2s]
         f = lambda t: None if t is None else t.contiguous().float()
@@ -124,7 +135,7 @@ class _Deform(torch.autograd.Function):
             a.grad_rot_base = g_rb.data_ptr()
         L.check(lib.a3d_deform_backward(C.byref(a), C.c_void_p(L.ptr(g_means)), C.c_void_p(L.ptr(g_scales)),
                                         C.c_void_p(L.ptr(g_rots)), L.stream_ptr()))
-        return (None, None, None, None, None, None, g_rb, *gp, *g1, *g2)
+        return (None, None, None, None, None, None, g_rb, *[_plane_grad_out(g, p) for g, p in zip(gp, planes)], *g1, *g2)
 
 
 def quat_to_matrix(q: torch.Tensor) -> torch.Tensor:

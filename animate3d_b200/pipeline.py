@@ -45,6 +45,35 @@ def get_camera(num_views: int, elevation: float = 15.0, azimuth_start: float = 0
     return torch.stack(out, 0)
 
 
+def tensor2vid(video: torch.Tensor, processor=None, output_type: str = "np"):
+    """pipeline.py:237-255: [B, C, F, H, W] in [-1, 1] -> per-batch frame lists.  `processor` (diffusers VaeImageProcessor) is
+    optional: its postprocess for these three output types is (x / 2 + 0.5).clamp(0, 1) -> NHWC (-> uint8 PIL)."""
+    import numpy as np
+    outputs = []
+    for b in range(video.shape[0]):
+        frames = video[b].permute(1, 0, 2, 3)                                 # [F, C, H, W]
+        if processor is not None:
+            outputs.append(processor.postprocess(frames, output_type))
+            continue
+        img = (frames / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            outputs.append(img)
+        else:
+            arr = img.detach().cpu().permute(0, 2, 3, 1).float().numpy()
+            if output_type == "np":
+                outputs.append(arr)
+            elif output_type == "pil":
+                from PIL import Image
+                outputs.append([Image.fromarray((a * 255).round().astype("uint8")) for a in arr])
+            else:
+                raise ValueError(f"{output_type} does not exist. Please choose one of ['np', 'pt', 'pil']")
+    if output_type == "np":
+        outputs = np.stack(outputs)
+    elif output_type == "pt":
+        outputs = torch.stack(outputs)
+    return outputs
+
+
 def _butterworth_lpf(shape, order=4, d_s=0.25, d_t=0.25, device="cpu"):
     T, H, W = shape[-3], shape[-2], shape[-1]
     t = torch.arange(T, device=device)[:, None, None].float()
@@ -84,6 +113,79 @@ class AnimateDiffMVI2VPipeline:
 
     def enable_vae_slicing(self):
         pass
+
+    # -------------------------------------------------------------------------------------------- conditioning encoders
+    # The CLIP text / image towers and the VAE are the reference's own third-party modules (transformers CLIPTextModel /
+    # CLIPVisionModelWithProjection, diffusers AutoencoderKL): they are injected, not re-implemented -- transformers is a
+    # library here exactly as it is in the reference.  Callables are accepted too (round-1 behaviour).
+    def encode_prompt(self, prompt, device=None, num_images_per_prompt: int = 1, do_classifier_free_guidance: bool = True,
+                      negative_prompt=None, prompt_embeds=None, negative_prompt_embeds=None, lora_scale=None, clip_skip=None):
+        """pipeline.py:345-512 without the LoRA / textual-inversion branches: tokenize (max_length, truncation), text encoder
+        (optionally the clip_skip hidden state through final_layer_norm), repeat per view, same for the negative prompt."""
+        device = device or self.device
+        if prompt_embeds is None:
+            if self.text_encoder is None:
+                raise ValueError("pass prompt_embeds or construct the pipeline with tokenizer + text_encoder")
+            if self.tokenizer is None:                                     # plain callable: (prompt, n) -> embeddings
+                return self.text_encoder(prompt, num_images_per_prompt), self.text_encoder(negative_prompt or "", num_images_per_prompt)
+            prompt_embeds = self._encode_text([prompt] if isinstance(prompt, str) else list(prompt), device, clip_skip)
+        bs, seq, _ = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.repeat(1, num_images_per_prompt, 1).view(bs * num_images_per_prompt, seq, -1)
+        if do_classifier_free_guidance and negative_prompt_embeds is None:
+            neg = [""] * bs if negative_prompt is None else ([negative_prompt] * bs if isinstance(negative_prompt, str) else list(negative_prompt))
+            if len(neg) != bs:
+                raise ValueError(f"`negative_prompt` has batch size {len(neg)}, but `prompt` has batch size {bs}")
+            negative_prompt_embeds = self._encode_text(neg, device, None)
+        if do_classifier_free_guidance:
+            negative_prompt_embeds = negative_prompt_embeds.to(prompt_embeds.dtype).repeat(1, num_images_per_prompt, 1).view(
+                bs * num_images_per_prompt, seq, -1)
+        return prompt_embeds, negative_prompt_embeds
+
+    def _encode_text(self, texts, device, clip_skip):
+        tok = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True, return_tensors="pt")
+        ids = tok.input_ids.to(device)
+        if clip_skip is None:
+            return self.text_encoder(ids)[0]
+        out = self.text_encoder(ids, output_hidden_states=True)
+        return self.text_encoder.text_model.final_layer_norm(out[-1][-(clip_skip + 1)])
+
+    def encode_image(self, image, device=None):
+        """pipeline.py:514-526: CLIP image embeds of the condition view(s) + their all-zero unconditional twin."""
+        device = device or self.device
+        if self.image_encoder is None:
+            raise ValueError("construct the pipeline with image_encoder (+ feature_extractor) or pass ip_adapter_image_embeds")
+        if not hasattr(self.image_encoder, "parameters"):                 # plain callable
+            emb = self.image_encoder(image)
+            return emb, torch.zeros_like(emb)
+        dtype = next(self.image_encoder.parameters()).dtype
+        if not isinstance(image, torch.Tensor):
+            image = self.feature_extractor(image, return_tensors="pt").pixel_values
+        emb = self.image_encoder(image.to(device=device, dtype=dtype)).image_embeds
+        return emb, torch.zeros_like(emb)
+
+    def encode_latents(self, image_size, image_list):
+        """pipeline.py:528-551: PIL condition images -> VAE latents * scaling_factor (resize to image_size[0], normalise to [-1,1])."""
+        import numpy as np
+        if self.vae is None:
+            raise ValueError("construct the pipeline with a VAE or pass first_frame_latents")
+        x = torch.stack([torch.from_numpy(np.array(im)) for im in image_list], 0).float() / 255
+        x = x.permute(0, 3, 1, 2)
+        x = torch.nn.functional.interpolate(x, size=(image_size[0], image_size[0] * x.shape[3] // x.shape[2]) if x.shape[2] <= x.shape[3]
+                                            else (image_size[0] * x.shape[2] // x.shape[3], image_size[0]), mode="bilinear",
+                                            antialias=True, align_corners=False)
+        x = (x - 0.5) / 0.5
+        with torch.no_grad():
+            lat = self.vae.encode(x.to(self.device)).latent_dist.sample()
+        return lat * self.vae.config.scaling_factor
+
+    def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
+        """pipeline.py:554-567: [B, 4, F, h, w] -> video [B, 3, F, 8h, 8w] in [-1, 1] (fp32)."""
+        if self.vae is None:
+            raise ValueError("construct the pipeline with a VAE to decode latents")
+        latents = latents / self.vae.config.scaling_factor
+        b, c, f, h, w = latents.shape
+        image = self.vae.decode(latents.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)).sample
+        return image[None].reshape((b, f, -1) + image.shape[2:]).permute(0, 2, 1, 3, 4).float()
 
     # -------------------------------------------------------------------------------------------- one denoise step
     def denoise_step(self, latents: torch.Tensor, t: int, prompt_embeds: torch.Tensor, camera: torch.Tensor,
@@ -170,7 +272,7 @@ class AnimateDiffMVI2VPipeline:
                  guidance_scale: float = 7.5, negative_prompt=None, num_videos_per_prompt: int = 1, eta: float = 0.0,
                  generator=None, latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
                  negative_prompt_embeds: Optional[torch.Tensor] = None, ip_adapter_image=None,
-                 ip_adapter_image_embeds: Optional[torch.Tensor] = None, output_type: str = "latent", return_dict: bool = True,
+                 ip_adapter_image_embeds: Optional[torch.Tensor] = None, output_type: str = "pil", return_dict: bool = True,
                  cross_attention_kwargs=None, clip_skip=None, callback_on_step_end: Optional[Callable] = None,
                  callback_on_step_end_tensor_inputs: List[str] = ("latents",), i2v_cond_time_zero: bool = False,
                  i2v_similarity_init=None, first_frame_latents: Optional[torch.Tensor] = None):
@@ -181,19 +283,13 @@ class AnimateDiffMVI2VPipeline:
             raise NotImplementedError("eta != 0 / i2v_similarity_init are unused by the released configuration")
         dev = self.device
         nv = num_videos_per_prompt
-        if prompt_embeds is None:
-            if self.text_encoder is None:
-                raise ValueError("pass prompt_embeds/negative_prompt_embeds or inject a text encoder callable")
-            prompt_embeds = self.text_encoder(prompt, nv)
-            negative_prompt_embeds = self.text_encoder(negative_prompt or "", nv)
+        if prompt_embeds is None or negative_prompt_embeds is None:
+            prompt_embeds, negative_prompt_embeds = self.encode_prompt(prompt, dev, nv, True, negative_prompt, prompt_embeds=prompt_embeds,
+                                                                       negative_prompt_embeds=negative_prompt_embeds, clip_skip=clip_skip)
         if ip_adapter_image_embeds is None:
-            if self.image_encoder is None:
-                raise ValueError("pass ip_adapter_image_embeds or inject an image encoder callable")
-            ip_adapter_image_embeds = self.image_encoder(ip_adapter_image)
+            ip_adapter_image_embeds, _ = self.encode_image(ip_adapter_image, dev)
         if first_frame_latents is None:
-            if self.vae is None:
-                raise ValueError("pass first_frame_latents or inject a VAE")
-            first_frame_latents = self.vae.encode_first_frames(ip_adapter_image, height, width)
+            first_frame_latents = self.encode_latents((height, width), ip_adapter_image)
         do_cfg = guidance_scale > 1.0
         if not do_cfg:
             raise NotImplementedError("the released sampler always runs with classifier-free guidance (guidance_scale 7.5)")
@@ -219,10 +315,13 @@ class AnimateDiffMVI2VPipeline:
                 if callback_on_step_end is not None:
                     res = callback_on_step_end(self, i, int(t), {"latents": lat})
                     lat = res.pop("latents", lat)
-        if output_type == "latent" or self.vae is None:
+        if output_type == "latent":
             video = lat
         else:
-            video = self.vae.decode_latents(lat)
+            if self.vae is None:
+                raise ValueError('output_type "pil" / "np" / "pt" needs a VAE; pass output_type="latent" to get the latents '
+                                 "(pipeline.py:1049-1056)")
+            video = tensor2vid(self.decode_latents(lat), getattr(self, "image_processor", None), output_type=output_type)
         return AnimateDiffMVI2VPipelineOutput(frames=video) if return_dict else (video,)
 
 

@@ -246,13 +246,16 @@ int a3d_deform_forward(const a3d_deform_args* args, float* means, float* scales,
 /* per-frame mean over the P gaussians of the k-planes feature vector (`hidden_feats.mean(0)`, gaussian_4d.py:501, 527):
  * featmean [T, num_scales*channels] */
 int a3d_deform_featmean(const a3d_deform_args* args, float* featmean, void* stream);
+/* Accumulates into args->grad_w1 / grad_w2 ([out, in] like the weights) and args->grad_planes.  grad_planes[i] is a
+ * CHANNEL-LAST scratch [plane_h[i], plane_w[i], channels] (zero it first; 16-byte aligned): the 16 channels of a texel are
+ * written with vector reductions; transpose it into the [1, channels, H, W] parameter gradient afterwards. */
 int a3d_deform_backward(const a3d_deform_args* args, const float* dL_dmeans, const float* dL_dscales, const float* dL_drotations,
                         void* stream);
 
 /* ---------------------------------------------------------------- ARAP regulariser -------------- */
 /* K nearest neighbours of every point among the same points, self excluded, squared distances ascending, ties by index:
  * pytorch3d.ops.knn_points(p, p, K=K+1)[..., 1:] as used by cal_connectivity_from_points
- * (custom/threestudio-animate3d/systems/util.py:79-82).  nbr [n,K] int32, dist2 [n,K]; K <= 8. */
+ * (custom/threestudio-animate3d/systems/util.py:79-82).  nbr [n,K] int32, dist2 [n,K]; K <= 12. */
 int a3d_knn_graph(const float* points, int n, int K, int32_t* nbr, float* dist2, void* stream);
 /* cal_arap_error (util.py:183-215) with estimate_rotation (138-173) fused, all frames in one launch:
  *   err = sum_{t>=1} sum_{i in sample} sum_n w[i,n] | e_in(t) - R_i(t) e_in(0) |^2,   e_in(t) = x_t[i] - x_t[nbr[i,n]],
@@ -268,10 +271,8 @@ int a3d_arap(const float* nodes, int Nt, int Nv, const int32_t* nbr, int K, cons
    The buffer must hold 8 + 4*32*8 uint64: words 8.. receive a clock64 timeline of four softmax warps of CTA (0,0,0) of the
    head-dim-40 kernel (tools/attn_timeline.py) */
 int a3d_debug_set_attn_trace(void* device_counter_u64);
-/* tuning hook of the head-dim-40 attention kernel: bits 0-3 = number (0..3) of every 4 score pairs whose exponential runs on
-   the FMA pipe (half2 polynomial) instead of MUFU.EX2; bits 4-7 = how many softmax warps of an SM sub-partition may be in their
-   exponential phase at once (XU turn-taking; 0 = unconstrained).  See csrc/a3d_attn.cu. */
-int a3d_debug_set_attn_poly(int poly_and_concurrency);
+/* tuning hook of the head-dim-40 attention kernel: 0 switches its one-step-ahead non-blocking barrier tests off (default on) */
+int a3d_debug_set_attn_poly(int early_tests);
 /* measurement hooks of the rasterizer (bench.py's splat roofline): with timing enabled every forward / backward records CUDA
    events at its stage boundaries; a3d_debug_raster_stage_ms returns the milliseconds of the last forward's stages
    [0] preprocess [1] scan + counts + duplicate [2] radix sort [3] tile ranges [4] render and the last backward's [5] render

@@ -12,28 +12,27 @@ from animate3d_b200 import _lib as L
 from tools import kernel_bench as kb
 
 lib = L.load()
-conc = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-poly = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-L.check(lib.a3d_debug_set_attn_poly(poly | (conc << 4) | (1 << 8)))
+early = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+L.check(lib.a3d_debug_set_attn_poly(early))
 buf = torch.zeros(8 + 4 * 32 * 8, dtype=torch.int64, device="cuda")
 kb.attn_case("warm", 2, 4, 16, 1024, 40)
 lib.a3d_debug_set_attn_trace(C.c_void_p(buf.data_ptr()))
-kb.attn_case(f"l0 cross-view conc={conc} poly={poly} (traced)", 2, 4, 16, 1024, 40)
+kb.attn_case(f"l0 cross-view early_tests={early} (traced)", 2, 4, 16, 1024, 40)
 lib.a3d_debug_set_attn_trace(C.c_void_p(None))
 t = buf[8:].cpu().view(4, 32, 8)
 t0 = int(t[:, 0, 0].min())
-names = ["top", "s_in_regs", "got_turn", "exp_done", "published"]
+names = ["top", "s_in_regs", "p_free", "exp_done", "published"]
 print("warp = (tile g, key half h); columns: cycles since the first warp's step 0")
 for j in list(range(4, 12)) + [20, 21, 30, 31]:
     for w in range(4):
         r = [int(x) - t0 for x in t[w, j, :5]]
         print(f"step {j:2d} warp(g={w >> 1},h={w & 1}) " + " ".join(f"{n}={v:7d}" for n, v in zip(names, r)) +
-              f" | wait+ldtm {r[1] - r[0]:5d} turn {r[2] - r[1]:5d} exp {r[3] - r[2]:5d} publish {r[4] - r[3]:5d}")
+              f" | wait+ldtm {r[1] - r[0]:5d} p_free {r[2] - r[1]:5d} exp {r[3] - r[2]:5d} publish {r[4] - r[3]:5d}")
 for w in range(4):
     d = t[w, 31, 4] - t[w, 8, 4]
     print(f"warp {w}: {int(d) / 23:.0f} cycles per step (steps 8..31)")
-ph = {"wait+ldtm": (0, 1), "turn": (1, 2), "exp": (2, 3), "publish": (3, 4)}
+ph = {"wait+ldtm": (0, 1), "p_free": (1, 2), "exp": (2, 3), "publish": (3, 4)}
 for k, (a, b) in ph.items():
     v = (t[:, 8:32, b] - t[:, 8:32, a]).float()
     print(f"{k:14s} mean {v.mean():7.0f}  min {v.min():7.0f}  max {v.max():7.0f}")
-L.check(lib.a3d_debug_set_attn_poly(1 << 8))
+L.check(lib.a3d_debug_set_attn_poly(1))
