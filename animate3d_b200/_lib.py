@@ -21,6 +21,7 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_int64), ("ldc", C.c_int64),
                 ("a_mode", C.c_int),
                 ("conv_n", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_c", C.c_int), ("conv_stride", C.c_int),
+                ("conv_nopad_lo", C.c_int),
                 ("bias", C.c_void_p), ("rowbias", C.c_void_p),
                 ("rb_ld", C.c_int64), ("rb_div", C.c_int64), ("rb_mod", C.c_int64),
                 ("acc_scale", C.c_float),

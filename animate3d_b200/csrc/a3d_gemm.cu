@@ -25,6 +25,8 @@ struct GemmDev {
   int tpi;        // output tiles per image (>=1) or 0 when several images share a tile
   int boh;        // output rows per tile
   int bimg;       // images per tile
+  int tpr;        // tiles per output row (> 1 when an output row is wider than the 128-row tile)
+  int conv_pad;   // zero padding in front of row / column 0 (1, or 0 for the asymmetric (0,1,0,1) padding of the VAE downsampler)
   // epilogue
   const float* bias;
   const float* rowbias;
@@ -144,9 +146,10 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
-        int img0 = 0, oh0 = 0;
+        int img0 = 0, oh0 = 0, ow0 = 0;
         if (p.a_mode == A3D_A_CONV3) {
-          if (p.tpi > 0) { img0 = mt / p.tpi; oh0 = (mt % p.tpi) * p.boh; }
+          if (p.tpr > 1) { img0 = mt / p.tpi; oh0 = (mt % p.tpi) / p.tpr; ow0 = ((mt % p.tpi) % p.tpr) * kBM; }
+          else if (p.tpi > 0) { img0 = mt / p.tpi; oh0 = (mt % p.tpi) * p.boh; }
           else { img0 = mt * p.bimg; oh0 = 0; }
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -155,7 +158,8 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           if (p.a_mode == A3D_A_CONV3) {
             const int tap = kb / p.cpb, c0 = (kb % p.cpb) * kBK;
             const int ky = tap / 3, kx = tap % 3;
-            tma_load_5d(smem_a + stage * Cfg::kABytes, &mapA, &full_bar[stage], c0, kx - 1, oh0 * p.conv_s + ky - 1, img0, 0);
+            tma_load_5d(smem_a + stage * Cfg::kABytes, &mapA, &full_bar[stage], c0, ow0 * p.conv_s + kx - p.conv_pad,
+                        oh0 * p.conv_s + ky - p.conv_pad, img0, 0);
           } else {
             tma_load_5d(smem_a + stage * Cfg::kABytes, &mapA, &full_bar[stage], kb * kBK, mt * kBM, 0, 0, 0);
           }
@@ -467,7 +471,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
 // ---------------------------------------------------------------------------------------------------------------
 // SIMT bring-up / reference kernel: same semantics, one thread per output element (also serves odd shapes)
 // ---------------------------------------------------------------------------------------------------------------
-struct SimtConv { int n, h, w, c, s, oh, ow; };
+struct SimtConv { int n, h, w, c, s, oh, ow, pad; };
 
 __global__ void gemm_simt_kernel(const GemmDev p, const __half* __restrict__ A, int64_t lda, const __half* __restrict__ B,
                                  SimtConv cv) {
@@ -486,7 +490,7 @@ __global__ void gemm_simt_kernel(const GemmDev p, const __half* __restrict__ A, 
       const int img = (int)(m / (cv.oh * cv.ow));
       const int oy = (int)((m / cv.ow) % cv.oh), ox = (int)(m % cv.ow);
       for (int tap = 0; tap < 9; ++tap) {
-        const int iy = oy * cv.s + tap / 3 - 1, ix = ox * cv.s + tap % 3 - 1;
+        const int iy = oy * cv.s + tap / 3 - cv.pad, ix = ox * cv.s + tap % 3 - cv.pad;
         if (iy < 0 || iy >= cv.h || ix < 0 || ix >= cv.w) continue;
         const __half* a = A + (((int64_t)img * cv.h + iy) * cv.w + ix) * cv.c;
         const __half* bb = b + (int64_t)tap * cv.c;
@@ -584,7 +588,7 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
     const int s = a->conv_stride;
     if (s != 1 && s != 2) return fail(A3D_EINVAL, "a3d_gemm: conv stride must be 1 or 2");
     if (a->conv_h % s || a->conv_w % s) return fail(A3D_EINVAL, "a3d_gemm: conv H/W must be multiples of the stride");
-    cv = SimtConv{a->conv_n, a->conv_h, a->conv_w, a->conv_c, s, a->conv_h / s, a->conv_w / s};
+    cv = SimtConv{a->conv_n, a->conv_h, a->conv_w, a->conv_c, s, a->conv_h / s, a->conv_w / s, a->conv_nopad_lo ? 0 : 1};
     if (a->K != 9LL * a->conv_c || a->M != (int64_t)cv.n * cv.oh * cv.ow)
       return fail(A3D_EINVAL, "a3d_gemm: conv geometry does not match M/K");
     d.conv_s = s;
@@ -597,18 +601,21 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
                ((reinterpret_cast<uintptr_t>(a->B) & 15) == 0) && (a->ldc % 16 == 0) &&
                ((reinterpret_cast<uintptr_t>(a->C) & 31) == 0);
   if (a->a_mode == A3D_A_PLAIN) tc_ok = tc_ok && (a->lda % 8 == 0) && a->lda >= a->K;
-  int boh = 0, bimg = 1, tpi = 0;
+  int boh = 0, bimg = 1, tpi = 0, tpr = 1;
   if (a->a_mode == A3D_A_CONV3) {
     tc_ok = tc_ok && (cv.c % kBK == 0);
     const int opix = cv.oh * cv.ow;
-    if (opix >= kBM) {
+    if (cv.ow > kBM) {           // wide images (VAE at 256^2): a tile is a 128-pixel piece of one output row
+      tc_ok = tc_ok && (cv.ow % kBM == 0);
+      boh = 1; tpr = cv.ow / kBM; tpi = cv.oh * tpr; bimg = 1;
+    } else if (opix >= kBM) {
       tc_ok = tc_ok && (opix % kBM == 0) && (kBM % cv.ow == 0);
       boh = kBM / cv.ow; tpi = opix / kBM; bimg = 1;
     } else {
       tc_ok = tc_ok && (kBM % opix == 0);
       boh = cv.oh; tpi = 0; bimg = kBM / (opix > 0 ? opix : 1);
     }
-    tc_ok = tc_ok && cv.ow * cv.s <= 256 && boh * cv.s <= 256;
+    tc_ok = tc_ok && (tpr > 1 ? kBM : cv.ow) * cv.s <= 256 && boh * cv.s <= 256;
   }
   if (a->R1) tc_ok = tc_ok && (a->ldr1 % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->R1) & 31) == 0);
   if (a->R2) tc_ok = tc_ok && (a->ldr2 % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->R2) & 31) == 0);
@@ -649,7 +656,7 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
   d.tiles_m = (int)((a->M + kBM - 1) / kBM);
   d.tiles_n = (int)((a->N + BN - 1) / BN);
   d.cpb = a->a_mode == A3D_A_CONV3 ? cv.c / kBK : 0;
-  d.tpi = tpi; d.boh = boh; d.bimg = bimg;
+  d.tpi = tpi; d.boh = boh; d.bimg = bimg; d.tpr = tpr; d.conv_pad = cv.pad;
   d.rb_stage = 0; d.rb_slots = 0;
   if (a->rowbias && (a->N % 4 == 0) && (a->rb_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(a->rowbias) & 15) == 0)) {
     if (d.rb_div % kBM == 0) { d.rb_stage = 1; d.rb_slots = 1; }                                  // one table row per tile
@@ -676,7 +683,7 @@ extern "C" int a3d_gemm(const a3d_gemm_args* a, void* stream) {
     const uint64_t img = (uint64_t)cv.h * cv.w * cv.c;
     const uint64_t dims[5] = {(uint64_t)cv.c, (uint64_t)cv.w, (uint64_t)cv.h, (uint64_t)cv.n, 1};
     const uint64_t str[4] = {(uint64_t)cv.c, (uint64_t)cv.w * cv.c, img, img * cv.n};
-    const uint32_t box[5] = {kBK, (uint32_t)(cv.ow * cv.s), (uint32_t)(boh * cv.s), (uint32_t)bimg, 1};
+    const uint32_t box[5] = {kBK, (uint32_t)((tpr > 1 ? kBM : cv.ow) * cv.s), (uint32_t)(boh * cv.s), (uint32_t)bimg, 1};
     MapKey ka = make_key(a->A, dims, str, box);
     ka.estr[1] = cv.s; ka.estr[2] = cv.s;
     if (int r = get_tensor_map(ka, &mapA)) return r;

@@ -233,6 +233,130 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   for (; r < r1; r += rows_par) emit(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld)), r);
 }
 
+// ------------------------------------------------------------------------------------------------ GroupNorm backward (d/dx only)
+// The VAE encoder sits on the SDS gradient path (animatemv_guidance.py:365-373): y = [silu](xhat * gamma + beta),
+// xhat = (x - mean) * rstd.  With g = dL/dy * silu'(.) * gamma:  dL/dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), the means over
+// the (rows x C/groups) elements of a (sample, group).  Same thread mapping and the same fixed-order reductions as the forward
+// (no atomics): pass 1 -> per (sample, chunk, group) partial sums, a warp per (sample, group) folds them, pass 2 applies.
+// mean / rstd come from the forward's statistics buffer.
+__device__ __forceinline__ float dsilu_f(float z) {
+  const float sg = 1.0f / (1.0f + __expf(-z));
+  return sg * (1.0f + z * (1.0f - sg));
+}
+
+template <bool kApply>
+__global__ void __launch_bounds__(512)
+gn_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ stats, const float* __restrict__ sums, float* __restrict__ partials, __half* __restrict__ dx,
+              int C, int rows_per_sample, int groups, int silu, int rows_par, int chunk_rows) {
+  extern __shared__ float sm[];  // pass 1: [rows_par][vpr][2 slots][2]
+  const int vpr = C / 8;
+  const int cpg = C / groups;
+  const int sample = blockIdx.y;
+  const int r0 = blockIdx.x * chunk_rows;
+  const int r1 = min(r0 + chunk_rows, rows_per_sample);
+  const int vec = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
+  const int c0 = vec * 8;
+  const int g0 = c0 / cpg, g1 = (c0 + 7) / cpg;
+  const int split = (g0 + 1) * cpg - c0;
+  float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+  if (rsub < rows_par) {
+    const int64_t row_base = (int64_t)sample * rows_per_sample;
+    const float2 sa = *reinterpret_cast<const float2*>(stats + ((int64_t)sample * groups + g0) * 2);   // (mean, rstd)
+    const float2 sb = *reinterpret_cast<const float2*>(stats + ((int64_t)sample * groups + g1) * 2);
+    float ga[8], be[8];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + c0)), b = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(beta + c0)), d = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+      ga[0] = a.x; ga[1] = a.y; ga[2] = a.z; ga[3] = a.w; ga[4] = b.x; ga[5] = b.y; ga[6] = b.z; ga[7] = b.w;
+      be[0] = c.x; be[1] = c.y; be[2] = c.z; be[3] = c.w; be[4] = d.x; be[5] = d.y; be[6] = d.z; be[7] = d.w;
+    }
+    float m1[2] = {0.f, 0.f}, m2[2] = {0.f, 0.f};
+    if (kApply) {
+      const float2 ta = *reinterpret_cast<const float2*>(sums + ((int64_t)sample * groups + g0) * 2);   // (mean g, mean g*xhat)
+      const float2 tb = *reinterpret_cast<const float2*>(sums + ((int64_t)sample * groups + g1) * 2);
+      m1[0] = ta.x; m2[0] = ta.y; m1[1] = tb.x; m2[1] = tb.y;
+    }
+    for (int r = r0 + rsub; r < r1; r += rows_par) {
+      const uint4 vx = __ldg(reinterpret_cast<const uint4*>(x + (row_base + r) * C + c0));
+      const uint4 vd = __ldg(reinterpret_cast<const uint4*>(dy + (row_base + r) * C + c0));
+      const __half2* hx = reinterpret_cast<const __half2*>(&vx);
+      const __half2* hd = reinterpret_cast<const __half2*>(&vd);
+      float out[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 fx = __half22float2(hx[i >> 1]), fd = __half22float2(hd[i >> 1]);
+        const float xv = (i & 1) ? fx.y : fx.x, dv = (i & 1) ? fd.y : fd.x;
+        const int sl = i >= split ? 1 : 0;
+        const float mean = sl ? sb.x : sa.x, rstd = sl ? sb.y : sa.y;
+        const float xh = (xv - mean) * rstd;
+        float g = dv * ga[i];
+        if (silu) g *= dsilu_f(fmaf(xh, ga[i], be[i]));
+        if (kApply) {
+          out[i] = rstd * (g - m1[sl] - xh * m2[sl]);
+        } else {
+          s1[sl] += g;
+          s2[sl] = fmaf(g, xh, s2[sl]);
+        }
+      }
+      if (kApply) {
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ow[i] = pack_f16x2(out[2 * i], out[2 * i + 1]);
+        *reinterpret_cast<uint4*>(dx + (row_base + r) * C + c0) = o;
+      }
+    }
+  }
+  if (kApply) return;
+  if (rsub < rows_par) {
+    float* o = sm + ((rsub * vpr + vec) * 2) * 2;
+    o[0] = s1[0]; o[1] = s2[0]; o[2] = s1[1]; o[3] = s2[1];
+  }
+  __syncthreads();
+  for (int stride = 1; stride < rows_par; stride *= 2) {      // fixed-order tree over the row lanes
+    if (rsub < rows_par && (rsub % (2 * stride)) == 0 && rsub + stride < rows_par) {
+      float* a = sm + ((rsub * vpr + vec) * 2) * 2;
+      const float* b = sm + (((rsub + stride) * vpr + vec) * 2) * 2;
+      a[0] += b[0]; a[1] += b[1]; a[2] += b[2]; a[3] += b[3];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const int v0 = (g * cpg) / 8, v1 = ((g + 1) * cpg - 1) / 8;
+    float a1 = 0.f, a2 = 0.f;
+    for (int v = v0; v <= v1; ++v) {
+      const int gv = (v * 8) / cpg;
+      const float* e = sm + (v * 2 + (gv == g ? 0 : 1)) * 2;
+      a1 += e[0]; a2 += e[1];
+    }
+    float* o = partials + (((int64_t)sample * gridDim.x + blockIdx.x) * groups + g) * 2;
+    o[0] = a1; o[1] = a2;
+  }
+}
+
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partials, int chunks, int groups, float inv_n, float* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int sample = blockIdx.y;
+  if (g >= groups) return;
+  float a1 = 0.f, a2 = 0.f;
+  for (int c = lane; c < chunks; c += 32) {
+    const float* e = partials + (((int64_t)sample * chunks + c) * groups + g) * 2;
+    a1 += e[0]; a2 += e[1];
+  }
+#pragma unroll
+  for (int off = 1; off < 32; off *= 2) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+  }
+  if (lane == 0) {
+    sums[((int64_t)sample * groups + g) * 2] = a1 * inv_n;
+    sums[((int64_t)sample * groups + g) * 2 + 1] = a2 * inv_n;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // C = 40 * LPR halves per row (320 / 640 / 1280 -> LPR = 8 / 16 / 32 lanes per row, 5 x 16 B per lane, all loads in flight);
 // a warp normalises 32 / LPR rows at once, statistics reduced over the LPR lanes with shuffles.
@@ -721,6 +845,35 @@ extern "C" int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, co
   gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __half*>(x1), c1, reinterpret_cast<const __half*>(x2), c2,
                                             gamma, beta, reinterpret_cast<__half*>(y), (int)rows_per_sample, groups, eps, silu,
                                             perm_a, perm_b, rows_par, chunk_rows, stats);
+  A3D_LAUNCH_CHECK();
+  return A3D_OK;
+}
+
+extern "C" int a3d_group_norm_backward(const void* x, int c, const float* gamma, const float* beta, const float* fwd_ws_stats,
+                                       const void* dy, void* dx, int64_t samples, int64_t rows_per_sample, int groups, int silu,
+                                       float* ws, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (c % groups || c % 8 || c / 8 > 1024 || groups > 64) return fail(A3D_EINVAL, "a3d_group_norm_backward: unsupported channels %d", c);
+  if (!x || !dy || !dx || !fwd_ws_stats || !ws) return fail(A3D_EINVAL, "a3d_group_norm_backward: null operand");
+  if (rows_per_sample > (int64_t)1 << 30 || samples > 65535) return fail(A3D_EINVAL, "a3d_group_norm_backward: extent too large");
+  const int vpr = c / 8;
+  int rows_par, threads, chunk_rows, chunks;
+  gn_geometry(c, samples, rows_per_sample, &rows_par, &threads, &chunk_rows, &chunks);
+  if (threads > 512) return fail(A3D_EINVAL, "a3d_group_norm_backward: C=%d too wide", c);
+  const size_t smem = (size_t)rows_par * vpr * 4 * sizeof(float);
+  float* sums = ws;                                           // [samples][groups][mean g, mean g*xhat]
+  float* partials = ws + 2 * (size_t)groups * samples;        // [samples][chunks][groups][2]   (fits a3d_group_norm_ws_bytes)
+  dim3 grid((unsigned)chunks, (unsigned)samples);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  const __half* dyh = reinterpret_cast<const __half*>(dy);
+  gn_bwd_kernel<false><<<grid, threads, smem, st>>>(xh, dyh, gamma, beta, fwd_ws_stats, nullptr, partials, nullptr, c, (int)rows_per_sample,
+                                                    groups, silu, rows_par, chunk_rows);
+  A3D_LAUNCH_CHECK();
+  const float inv_n = 1.0f / ((float)rows_per_sample * (float)(c / groups));
+  gn_bwd_finalize_kernel<<<dim3((groups + 7) / 8, (unsigned)samples), 256, 0, st>>>(partials, chunks, groups, inv_n, sums);
+  A3D_LAUNCH_CHECK();
+  gn_bwd_kernel<true><<<grid, threads, 0, st>>>(xh, dyh, gamma, beta, fwd_ws_stats, sums, nullptr, reinterpret_cast<__half*>(dx), c,
+                                                (int)rows_per_sample, groups, silu, rows_par, chunk_rows);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }

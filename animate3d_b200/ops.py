@@ -21,7 +21,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          conv: Optional[Tuple[int, int, int, int, int]] = None, bias=None, rowbias=None, rb_div: int = 1, rb_mod: int = 0,
          rb_ld: int = 0,
          acc_scale: float = 1.0, R1=None, ldr1: int = 0, r1_scale: float = 1.0, R2=None, ldr2: int = 0, geglu: bool = False,
-         out_f32: bool = False, perm: Tuple[int, int] = (0, 0), impl: int = L.IMPL_AUTO) -> torch.Tensor:
+         out_f32: bool = False, perm: Tuple[int, int] = (0, 0), impl: int = L.IMPL_AUTO, conv_nopad_lo: bool = False) -> torch.Tensor:
     """out = epilogue(A @ B^T); see a3d_gemm in include/a3d.h.  `conv` = (n_img, H, W, C, stride) selects the implicit
     3x3 convolution A operand."""
     lib = L.load()
@@ -34,6 +34,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     if conv is not None:
         a.a_mode = L.A_CONV3
         a.conv_n, a.conv_h, a.conv_w, a.conv_c, a.conv_stride = conv
+        a.conv_nopad_lo = int(conv_nopad_lo)
     else:
         a.a_mode = L.A_PLAIN
     a.bias = L.ptr(bias)
@@ -95,6 +96,15 @@ def group_norm(x1, c1, x2, c2, gamma, beta, y, samples, rows_per_sample, groups,
                                C.c_int64(rows_per_sample), groups, C.c_float(eps), int(silu), C.c_int64(perm[0]),
                                C.c_int64(perm[1]), C.c_void_p(ws_stats.data_ptr()), L.stream_ptr()))
     return y
+
+
+def group_norm_backward(x, c, gamma, beta, fwd_stats, dy, dx, samples, rows_per_sample, groups, silu, ws):
+    lib = L.load()
+    L.check(lib.a3d_group_norm_backward(C.c_void_p(x.data_ptr()), c, C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()),
+                                        C.c_void_p(fwd_stats.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dx.data_ptr()),
+                                        C.c_int64(samples), C.c_int64(rows_per_sample), groups, int(silu), C.c_void_p(ws.data_ptr()),
+                                        L.stream_ptr()))
+    return dx
 
 
 def layer_norm(x, gamma, beta, y, rows, c, eps=1e-5):

@@ -59,6 +59,8 @@ typedef struct a3d_gemm_args {
   int64_t lda, ldc;   /* elements; lda ignored for CONV3 */
   int a_mode;
   int conv_n, conv_h, conv_w, conv_c, conv_stride; /* CONV3 geometry (input) */
+  int conv_nopad_lo;          /* CONV3: 0 = zero padding 1 on every side (UNet); 1 = no padding in front of row / column 0 and 1 behind
+                                 the last ones = F.pad(x, (0,1,0,1)) + conv(padding=0), the SD-VAE Downsample2D */
   const float* bias;          /* [N] or NULL */
   const float* rowbias;       /* [rb_rows, rb_ld] or NULL */
   int64_t rb_ld, rb_div, rb_mod;
@@ -133,6 +135,11 @@ size_t a3d_group_norm_ws_bytes(int64_t samples, int64_t rows_per_sample, int c, 
 int a3d_group_norm(const void* x1, int c1, const void* x2, int c2, const float* gamma, const float* beta, void* y,
                    int64_t samples, int64_t rows_per_sample, int groups, float eps, int silu, int64_t perm_a,
                    int64_t perm_b, float* ws_stats, void* stream);
+/* Input gradient of GroupNorm(+SiLU) for the VAE encoder on the SDS gradient path (animatemv_guidance.py:365-373; weights are
+ * frozen, 301-302).  x / dy / dx: NHWC fp16 [samples * rows_per_sample, c]; fwd_ws_stats: the first 2*groups*samples floats of the
+ * forward call's ws_stats ((mean, rstd) per (sample, group)); ws: scratch of a3d_group_norm_ws_bytes(...) bytes. */
+int a3d_group_norm_backward(const void* x, int c, const float* gamma, const float* beta, const float* fwd_ws_stats, const void* dy,
+                            void* dx, int64_t samples, int64_t rows_per_sample, int groups, int silu, float* ws, void* stream);
 /* LayerNorm over C per row: BasicTransformerBlock.norm1/2/3 of the spatial and temporal transformers (diffusers). */
 int a3d_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int c, float eps,
                    void* stream);

@@ -121,6 +121,8 @@ CONV_CASES = [
     (4, 32, 32, 64, 128, 2),
     (8, 16, 16, 128, 128, 2),
     (8, 8, 8, 64, 128, 2),
+    (2, 256, 256, 128, 128, 1),      # VAE level 0: an output row (256 px) is wider than the 128-row tile
+    (1, 256, 256, 64, 64, 1),
 ]
 
 
@@ -144,6 +146,29 @@ def test_conv3x3(case, impl):
                    stride=s, padding=1)
     ref = ref.permute(0, 2, 3, 1).reshape(M, Cout)
     close(out, ref, what=f"conv {case} {impl}")
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("case", [(2, 256, 256, 128, 128), (3, 64, 64, 256, 256), (4, 16, 16, 64, 128)], ids=lambda c: "n%d_%dx%d_c%d_o%d" % c)
+def test_conv3x3_stride2_asymmetric_padding(case, impl):
+    """SD-VAE Downsample2D: F.pad(x, (0, 1, 0, 1)) then conv(stride 2, padding 0) -- `conv_nopad_lo`."""
+    ops, L = _ops()
+    n, H, W, Cin, Cout = case
+    if impl == "simt" and H > 64:
+        pytest.skip("SIMT reference kernel only checked on the small cases")
+    g = torch.Generator(device=DEV).manual_seed(sum(case))
+    x = (torch.randn(n, H, W, Cin, device=DEV, generator=g) * 0.5).half()
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) * 0.05
+    bias = torch.randn(Cout, device=DEV, generator=g)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().half()
+    M = n * (H // 2) * (W // 2)
+    out = torch.zeros(M, Cout, device=DEV, dtype=torch.float16)
+    ops.gemm(x, wk, out, M=M, N=Cout, K=9 * Cin, conv=(n, H, W, Cin, 2), bias=bias, conv_nopad_lo=True,
+             impl=L.IMPL_TC if impl == "tc" else L.IMPL_SIMT)
+    torch.cuda.synchronize()
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xp, wk.float().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2), bias, stride=2, padding=0)
+    close(out, ref.permute(0, 2, 3, 1).reshape(M, Cout), what=f"vae downsample conv {case} {impl}")
 
 
 # ------------------------------------------------------------------------------------------------------------ attention
@@ -328,6 +353,37 @@ def test_group_norm_large_mean_small_variance(case):
     ref = F.group_norm(xr, 32, gamma.double(), beta.double(), 1e-5).permute(0, 2, 1).reshape(samples * rps, c)
     torch.cuda.synchronize()
     close(y, ref.float(), what=f"group_norm large mean {case}")
+
+
+@pytest.mark.parametrize("case", [(3, 1024, 128), (2, 4096, 256), (4, 256, 512), (2, 65536, 128)], ids=lambda c: "s%d_r%d_c%d" % c)
+@pytest.mark.parametrize("silu", [0, 1])
+def test_group_norm_backward(case, silu):
+    """d/dx of GroupNorm(32, eps 1e-6)(+SiLU) -- the VAE encoder's norms on the SDS gradient path -- vs torch autograd."""
+    ops, _ = _ops()
+    samples, rps, c = case
+    g = torch.Generator(device=DEV).manual_seed(sum(case) + silu)
+    x = (torch.randn(samples * rps, c, device=DEV, generator=g) * 1.3 + 0.2).half()
+    dy = torch.randn(samples * rps, c, device=DEV, generator=g).half()
+    gamma = torch.randn(c, device=DEV, generator=g)
+    beta = torch.randn(c, device=DEV, generator=g)
+    y = torch.empty_like(x)
+    ws = torch.empty(ops.group_norm_ws_floats(samples, rps, c, 32), device=DEV)
+    ops.group_norm(x, c, None, 0, gamma, beta, y, samples, rps, 32, 1e-6, silu, ws)
+    stats = ws[: 2 * 32 * samples].clone()
+    dx = torch.empty_like(x)
+    ws2 = torch.empty_like(ws)
+    ops.group_norm_backward(x, c, gamma, beta, stats, dy, dx, samples, rps, 32, silu, ws2)
+    xr = x.float().reshape(samples, rps, c).permute(0, 2, 1).clone().requires_grad_(True)
+    ref = F.group_norm(xr, 32, gamma, beta, 1e-6)
+    if silu:
+        ref = F.silu(ref)
+    ref.backward(dy.float().reshape(samples, rps, c).permute(0, 2, 1))
+    want = xr.grad.permute(0, 2, 1).reshape(samples * rps, c)
+    torch.cuda.synchronize()
+    close(dx, want, what=f"group_norm backward {case} silu={silu}")
+    dx2 = torch.empty_like(x)
+    ops.group_norm_backward(x, c, gamma, beta, stats, dy, dx2, samples, rps, 32, silu, ws2)
+    assert torch.equal(dx, dx2)
 
 
 @pytest.mark.parametrize("c", [320, 640, 1280])
