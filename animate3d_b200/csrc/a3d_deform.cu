@@ -65,23 +65,19 @@ deform_kernel(DeformGrids G, DeformMlp M, DeformGlobal X, const float* __restric
               const float* __restrict__ g_means, const float* __restrict__ g_scales, const float* __restrict__ g_rots) {
   constexpr bool kBackward = false;
   static_assert(kMode == 0 || kMode == 2, "backward is a separate kernel");
-  extern __shared__ float sm[];
-  // shared copies of the MLP weights (and, in backward, of their gradient accumulators)
+  extern __shared__ __align__(16) float sm[];
+  // shared copies of the MLP weights
   float* sw1 = sm;                                   // [3][32][32]
   float* sw2 = sw1 + 3 * kHid * kHid;                // [3][4][32] (padded to 4 outputs)
-  float* sg1 = sw2 + 3 * 4 * kHid;                   // backward only
-  float* sg2 = sg1 + 3 * kHid * kHid;
   const int nfeat = G.scales * kFeat;
   if (kMode != 2) {
     for (int i = threadIdx.x; i < 3 * kHid * kHid; i += blockDim.x) {
       const int m = i / (kHid * kHid), r = i % (kHid * kHid);
       sw1[i] = (r % kHid < nfeat) ? M.w1[m][(r / kHid) * nfeat + r % kHid] : 0.f;
-      if (kBackward) sg1[i] = 0.f;
     }
     for (int i = threadIdx.x; i < 3 * 4 * kHid; i += blockDim.x) {
       const int m = i / (4 * kHid), r = (i % (4 * kHid)) / kHid, c = i % kHid;
       sw2[i] = r < out_dim(m) ? M.w2[m][r * kHid + c] : 0.f;
-      if (kBackward) sg2[i] = 0.f;
     }
   } else {
     for (int i = threadIdx.x; i < 2 * kHid; i += blockDim.x) sm[i] = 0.f;   // [2 frames a block may straddle][32]
@@ -133,22 +129,34 @@ deform_kernel(DeformGrids G, DeformMlp M, DeformGlobal X, const float* __restric
     return;
   }
   // ---- three MLPs
-  float hid[3][kHid];
+  // the weights are broadcast reads from shared memory: 16-byte loads (4 FMAs per load) -- with scalar loads the kernel sat on
+  // the shared-memory pipe (one LDS per FMA: 0.68 ms for 16 frames x 50k gaussians, profiles/r02_splat_launches.txt)
   float outv[3][4];
-#pragma unroll
+#pragma unroll 1
   for (int m = 0; m < 3; ++m) {
+    float hid[kHid];
 #pragma unroll
     for (int r = 0; r < kHid; ++r) {
       float a = 0.f;
+      const float4* wr = reinterpret_cast<const float4*>(sw1 + (m * kHid + r) * kHid);
 #pragma unroll
-      for (int c = 0; c < kHid; ++c) a = fmaf(sw1[(m * kHid + r) * kHid + c], feat[c], a);
-      hid[m][r] = fmaxf(a, 0.f);
+      for (int c = 0; c < kHid / 4; ++c) {
+        const float4 w4 = wr[c];
+        a = fmaf(w4.x, feat[4 * c], a); a = fmaf(w4.y, feat[4 * c + 1], a);
+        a = fmaf(w4.z, feat[4 * c + 2], a); a = fmaf(w4.w, feat[4 * c + 3], a);
+      }
+      hid[r] = fmaxf(a, 0.f);
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       float a = 0.f;
+      const float4* wr = reinterpret_cast<const float4*>(sw2 + (m * 4 + r) * kHid);
 #pragma unroll
-      for (int c = 0; c < kHid; ++c) a = fmaf(sw2[(m * 4 + r) * kHid + c], hid[m][c], a);
+      for (int c = 0; c < kHid / 4; ++c) {
+        const float4 w4 = wr[c];
+        a = fmaf(w4.x, hid[4 * c], a); a = fmaf(w4.y, hid[4 * c + 1], a);
+        a = fmaf(w4.z, hid[4 * c + 2], a); a = fmaf(w4.w, hid[4 * c + 3], a);
+      }
       outv[m][r] = a;
     }
   }
@@ -260,8 +268,13 @@ deform_backward_kernel(DeformGrids G, DeformMlp M, DeformGlobal X, const float* 
 #pragma unroll
       for (int r = 0; r < kHid; ++r) {
         float a = 0.f;
+        const float4* wr = reinterpret_cast<const float4*>(sw1 + (m * kHid + r) * kHid);
 #pragma unroll
-        for (int c = 0; c < kHid; ++c) a = fmaf(sw1[(m * kHid + r) * kHid + c], feat[c], a);
+        for (int c = 0; c < kHid / 4; ++c) {
+          const float4 w4 = wr[c];
+          a = fmaf(w4.x, feat[4 * c], a); a = fmaf(w4.y, feat[4 * c + 1], a);
+          a = fmaf(w4.z, feat[4 * c + 2], a); a = fmaf(w4.w, feat[4 * c + 3], a);
+        }
         hid[r] = fmaxf(a, 0.f);
       }
       float outv[4], dout[4] = {0.f, 0.f, 0.f, 0.f};
@@ -301,13 +314,12 @@ deform_backward_kernel(DeformGrids G, DeformMlp M, DeformGlobal X, const float* 
 #pragma unroll
       for (int c = 0; c < kHid; c += 4) {
         float4 d4 = *reinterpret_cast<float4*>(s_df + threadIdx.x * kLdS + c);
-        float add[4];
+        float add[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float a = 0.f;
-#pragma unroll
-          for (int r = 0; r < kHid; ++r) a = fmaf(sw1[(m * kHid + r) * kHid + c + k], dh[r], a);
-          add[k] = a;
+        for (int r = 0; r < kHid; ++r) {
+          const float4 w4 = *reinterpret_cast<const float4*>(sw1 + (m * kHid + r) * kHid + c);
+          add[0] = fmaf(w4.x, dh[r], add[0]); add[1] = fmaf(w4.y, dh[r], add[1]);
+          add[2] = fmaf(w4.z, dh[r], add[2]); add[3] = fmaf(w4.w, dh[r], add[3]);
         }
         d4.x += add[0]; d4.y += add[1]; d4.z += add[2]; d4.w += add[3];
         *reinterpret_cast<float4*>(s_df + threadIdx.x * kLdS + c) = d4;

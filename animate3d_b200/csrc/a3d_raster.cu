@@ -182,10 +182,15 @@ raster_render_backward_kernel(RasterDev a, RasterWs ws, const float* __restrict_
   }
 }
 
+__global__ void raster_keys_export_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ((in[i] >> 31) << 32) | (in[i] & 0x7FFFFFFFull);
+}
+
 static int sort_bits(long long total_tiles) {
   int b = 0;
   while ((1ll << b) <= total_tiles) ++b;
-  return 32 + (b < 1 ? 1 : b);
+  return 31 + (b < 1 ? 1 : b);   // key = (global tile << 31) | depth bits without the (always zero) sign bit
 }
 
 static size_t cub_temp_bytes(int n_scan, long long cap, int end_bit) {
@@ -347,7 +352,10 @@ extern "C" int a3d_raster_binning_tap(const void* workspace, int P, int H, int W
   carve_workspace(const_cast<void*>(workspace), P, H, W, num_cams, max_rendered, cub, &ws);
   // raw copies of the global sorted tables; the host wrapper slices camera `cam` out of them using the counters
   (void)cam;
-  if (keys_out) A3D_CUDA_CHECK(cudaMemcpyAsync(keys_out, ws.keys_b, (size_t)max_rendered * 8, cudaMemcpyDeviceToDevice, st));
+  if (keys_out) {   // external form of a key: (tile << 32) | depth bits (the upstream rasterizer's layout)
+    raster_keys_export_kernel<<<(unsigned)((max_rendered + 255) / 256), 256, 0, st>>>(ws.keys_b, keys_out, max_rendered);
+    A3D_LAUNCH_CHECK();
+  }
   if (point_list_out) A3D_CUDA_CHECK(cudaMemcpyAsync(point_list_out, ws.vals_b, (size_t)max_rendered * 4, cudaMemcpyDeviceToDevice, st));
   if (ranges_out) A3D_CUDA_CHECK(cudaMemcpyAsync(ranges_out, ws.ranges, (size_t)num_cams * gx * gy * 8, cudaMemcpyDeviceToDevice, st));
   return A3D_OK;

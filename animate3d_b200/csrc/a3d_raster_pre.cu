@@ -91,7 +91,7 @@ __global__ void raster_duplicate_kernel(RasterDev a, RasterWs ws, int gx, int nu
     for (int x = r.x; x < r.z; ++x) {
       if (off < cap) {
         const uint64_t tile = (uint64_t)cam * num_tiles + (uint64_t)(y * gx + x);
-        ws.keys_a[off] = (tile << 32) | dbits;
+        ws.keys_a[off] = (tile << 31) | dbits;     // depth > 0.2: the sign bit is always 0 and is not sorted (one radix pass less)
         ws.vals_a[off] = (uint32_t)i;
       }
       ++off;
@@ -101,10 +101,10 @@ __global__ void raster_duplicate_kernel(RasterDev a, RasterWs ws, int gx, int nu
 __global__ void raster_ranges_kernel(RasterWs ws, long long n, long long total_tiles) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  const uint64_t tile = ws.keys_b[idx] >> 32;
+  const uint64_t tile = ws.keys_b[idx] >> 31;
   if (tile >= (uint64_t)total_tiles) return;   // padding key
-  if (idx == 0 || (ws.keys_b[idx - 1] >> 32) != tile) ws.ranges[tile].x = (uint32_t)idx;
-  if (idx == n - 1 || (ws.keys_b[idx + 1] >> 32) != tile) ws.ranges[tile].y = (uint32_t)(idx + 1);
+  if (idx == 0 || (ws.keys_b[idx - 1] >> 31) != tile) ws.ranges[tile].x = (uint32_t)idx;
+  if (idx == n - 1 || (ws.keys_b[idx + 1] >> 31) != tile) ws.ranges[tile].y = (uint32_t)(idx + 1);
 }
 
 // per-gaussian backward: (dconic, dmean2D, ddepth, drgb) of every camera -> means3D / scales / rotations / colors / SH

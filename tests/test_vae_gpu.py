@@ -126,13 +126,15 @@ def test_guidance_sds_gradient_reaches_the_rendered_images():
     # same random draws as the engine run: the CUDA generator was seeded, so replay its draws on the CPU explicitly
     torch.manual_seed(noise_seed)
     n1 = torch.randn(bnf, 4, 32, 32, device="cuda").cpu()
-    n2 = torch.randn(1, nv, 4, nf - 1, 32, 32, device="cuda").cpu()
+    # the forward-diffusion noise is `randn_like` of a permuted VIEW (frames 1.. of "b n c f h w"): same strides, same stream
+    rest_like = torch.empty(bnf, 4, 32, 32, device="cuda").reshape(1, nv, nf, 4, 32, 32).permute(0, 1, 3, 2, 4, 5)[:, :, :, 1:]
+    n2 = torch.randn_like(rest_like).cpu()
     x = torch.nn.functional.interpolate(rgb_o.permute(0, 3, 1, 2), (256, 256), mode="bilinear", align_corners=False)
     mo = VO.encode_moments(vsd, vcfg, x * 2 - 1)
     lat = VO.sample_latents(mo, n1) * 0.18215
     loss_o, _ = ref._recon_loss(lat, t, torch.cat([text[None].expand(nv, -1, -1), unc[None].expand(nv, -1, -1)]), c2w, img, noise=n2)
     loss_o.backward()
-    rl = abs(float(out["loss_sds"]) - float(loss_o)) / abs(float(loss_o))
+    rl = abs(float(out["loss_sds"].detach()) - float(loss_o.detach())) / abs(float(loss_o.detach()))
     rg = _rel(rgb_g.grad, rgb_o.grad)
     print(f"guidance through the engine: loss {float(out['loss_sds']):.5f} vs {float(loss_o):.5f} (rel {rl:.2e}), d loss / d rgb rel-l2 {rg:.3e}")
     assert rl < 2e-2 and rg < 5e-2
