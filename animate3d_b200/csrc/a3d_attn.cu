@@ -727,7 +727,11 @@ struct Attn5Cfg {
 };
 
 // POLY: how many of the 4 fp16x2 pairs of every 8-key chunk take exp2 on the FMA pipe (exp2_fma) instead of MUFU.
-template <int D>
+// TS: the probabilities of a step go to TENSOR MEMORY (tcgen05.st) and the P V product reads its A operand from there
+//   (tcgen05.mma [d], [a_tmem], b_desc): no swizzled shared-memory stores, no fence.proxy.async / MEMBAR per step.  TMEM then holds
+//   S[g] single-buffered at column g*64 (S(j) sits in registers right after the step starts, so QK^T(j+1) has a whole step to
+//   land), P[g][b] (64 keys = 32 packed columns) at 128 + (2g+b)*32, O[g][h] at 256 + (2g+h)*64.
+template <int D, bool TS>
 __global__ void __launch_bounds__(640, 1)
 attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV) {
@@ -850,37 +854,45 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       const uint64_t dk = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t dv = make_smem_desc_sw128(smem_u32(sV), Cfg::kKVBox, 1024);   // MN-major: next 64 columns one box on
       const uint64_t dp = make_smem_desc_sw128(smem_u32(sP + 2 * g * Cfg::kPBox), 16, 1024);
-      const uint32_t tS = tmem_base + 2 * g * 64, tO = tmem_base + 256 + 2 * g * 64;
-      auto issue_qk = [&](int j) {      // S[g][j&1] = Q_g K_j^T; the K stage is released as soon as these MMAs retire
+      const uint32_t tS = tmem_base + (TS ? g * 64 : 2 * g * 64), tO = tmem_base + 256 + 2 * g * 64;
+      const uint32_t tP = tmem_base + 128 + 2 * g * 32;     // TS only
+      auto issue_qk = [&](int j) {      // S[g][j&1] (TS: S[g]) = Q_g K_j^T; the K stage is released as soon as these MMAs retire
         const uint64_t kb_ = dk + (uint64_t)((j % S) * ((Cfg::kQB * Cfg::kKVBox) >> 4));
 #pragma unroll
         for (int kk = 0; kk < Cfg::kDqk / 16; ++kk)
-          umma_f16(tS + (j & 1) * 64, dq + (uint64_t)((kk / 4) * (Cfg::kQBox >> 4) + 2 * (kk % 4)),
+          umma_f16(tS + (TS ? 0 : (j & 1) * 64), dq + (uint64_t)((kk / 4) * (Cfg::kQBox >> 4) + 2 * (kk % 4)),
                    kb_ + (uint64_t)((kk / 4) * (Cfg::kKVBox >> 4) + 2 * (kk % 4)), idesc_qk, kk ? 1u : 0u);
-        umma_commit(&s_full[2 * g + (j & 1)]);
+        umma_commit(&s_full[2 * g + (TS ? 0 : (j & 1))]);
         umma_commit(&k_empty[j % S]);
       };
       auto issue_pv = [&](int j, int hh) {      // O_g,hh += P_g(j)[:, 32 hh .. 32 hh + 31] V_j[32 hh .. 32 hh + 31, :]
         const uint64_t pb_ = dp + (uint64_t)((j & 1) * (Cfg::kPBox >> 4));
         const uint64_t vb_ = dv + (uint64_t)((j % S) * ((Cfg::kVB * Cfg::kKVBox) >> 4));
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-          umma_f16(tO + hh * 64, pb_ + (uint64_t)(2 * (2 * hh + kk)), vb_ + (uint64_t)(128 * (2 * hh + kk)), idesc_pv,
-                   (j | kk) ? 1u : 0u);
+        for (int kk = 0; kk < 2; ++kk) {
+          if (TS)   // A = P[g][j&1] in TMEM: 16 keys = 8 packed columns per MMA
+            umma_f16_ts(tO + hh * 64, tP + (j & 1) * 32 + (2 * hh + kk) * 8, vb_ + (uint64_t)(128 * (2 * hh + kk)), idesc_pv,
+                        (j | kk) ? 1u : 0u);
+          else
+            umma_f16(tO + hh * 64, pb_ + (uint64_t)(2 * (2 * hh + kk)), vb_ + (uint64_t)(128 * (2 * hh + kk)), idesc_pv,
+                     (j | kk) ? 1u : 0u);
+        }
         umma_commit(&pv_done[(2 * g + hh) * 2 + (j & 1)]);
       };
       mbar_wait(q_full, 0);
-      for (int j0 = 0; j0 < 2 && j0 < n; ++j0) {
+      constexpr int kAhead = TS ? 1 : 2;       // QK^T runs this many steps ahead of the softmax
+      for (int j0 = 0; j0 < kAhead && j0 < n; ++j0) {
         mbar_wait(&k_full[j0 % S], (j0 / S) & 1);
         tc_fence_after();
         issue_qk(j0);
       }
       for (int j = 0; j < n; ++j) {
-        if (j + 2 < n) {
-          mbar_wait(&s_free[2 * g + (j & 1)], (j >> 1) & 1);
-          mbar_wait(&k_full[(j + 2) % S], ((j + 2) / S) & 1);
+        if (j + kAhead < n) {
+          if (TS) mbar_wait(&s_free[2 * g], j & 1);                   // S(j) is in the softmax warps' registers
+          else mbar_wait(&s_free[2 * g + (j & 1)], (j >> 1) & 1);
+          mbar_wait(&k_full[(j + kAhead) % S], ((j + kAhead) / S) & 1);
           tc_fence_after();
-          issue_qk(j + 2);
+          issue_qk(j + kAhead);
         }
         mbar_wait(&v_full[j % S], (j / S) & 1);
 #pragma unroll
@@ -921,20 +933,22 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       bool s_ok = false, p_ok = true;
       for (int j = 0; j < n; ++j) {
         const int valid = ((j == n - 1) ? p.rows_k : rows_tile) - 32 * h;   // valid keys among this half's 32 columns
-        const int b = 2 * g + (j & 1);
+        const int b = 2 * g + (j & 1);                                 // P buffer (and, without TS, S buffer) of this step
+        const int sb_ = TS ? 2 * g : b;                                // S barrier / buffer index
+        const uint32_t s_par = TS ? (uint32_t)(j & 1) : (uint32_t)((j >> 1) & 1);
         // debug timeline (tools/attn_timeline.py): the four softmax warps of SM sub-partition 0 of CTA (0,0,0), 32 steps
         const bool tr = p.dbg && j < 32 && quad == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
         unsigned long long* trow = p.dbg + 8 + ((warp >> 2) * 32 + j) * 8;
         if (tr) trow[0] = clock64();
-        if (!(p.early_test && s_ok)) mbar_wait(&s_full[b], (j >> 1) & 1);
+        if (!(p.early_test && s_ok)) mbar_wait(&s_full[sb_], s_par);
         tc_fence_after();
         uint32_t s[32];
-        tmem_ld32(tmem_base + lane_addr + b * 64 + 32 * h, s);
+        tmem_ld32(tmem_base + lane_addr + (TS ? g * 64 : b * 64) + 32 * h, s);
         tmem_wait_ld();
         if (tr) trow[1] = clock64();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[b]);   // S buffer may be overwritten by QK^T(j+2)
+        if (lane == 0) mbar_arrive(&s_free[sb_]);   // S buffer may be overwritten by the next QK^T into it
         if (valid < 32) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -952,7 +966,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         const uint32_t sPg = sP_u32 + b * Cfg::kPBox;
         if (j >= 2 && !(p.early_test && p_ok)) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);   // P columns of step j-2 consumed
         if (p.early_test) {   // tests for step j+1, consumed at its top
-          s_ok = j + 1 < n && mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1);
+          s_ok = j + 1 < n && (TS ? mbar_test(&s_full[2 * g], (j + 1) & 1) : mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1));
           p_ok = j + 1 < 2 || mbar_test(&my_pv_done[(j + 1) & 1], ((j - 1) >> 1) & 1);
         }
         if (tr) trow[2] = clock64();
@@ -963,6 +977,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           // fp16) is the step redone with the updated stabiliser -- after the first few steps that never happens.
           float mx0 = -INFINITY, mx1 = -INFINITY;
           const uint64_t nm2 = pack2(kPBias - m_run, kPBias - m_run);
+          uint32_t pk[16];           // TS: the 32 probabilities of this thread's row, key pairs packed (even key in the low half)
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
             uint4 q;
@@ -975,9 +990,11 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
               float y0, y1;
               unpack2(ffma2(pack2u(s[i], s[i + 1]), sc2, nm2), y0, y1);
               qw[t] = pack_f16x2(ex2_approx(y0), ex2_approx(y1));
+              if (TS) pk[c16 * 4 + t] = qw[t];
             }
-            st_shared_v4(sPg + p_off[c16], q);
+            if (!TS) st_shared_v4(sPg + p_off[c16], q);
           }
+          if (TS) tmem_st16(tmem_base + lane_addr + 128 + (uint32_t)(b * 32 + h * 16), pk);
           if (pass > 0 || j == 0) break;
           const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
           if (!__any_sync(0xffffffffu, m_new - m_run > kRescale5)) break;
@@ -1000,7 +1017,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           m_run = m_up;
         }
         if (tr) trow[3] = clock64();
-        fence_proxy_async_smem();
+        if (TS) tmem_wait_st(); else fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&my_p_full[j & 1]);
@@ -1440,7 +1457,7 @@ static int tile_geom_k64(const a3d_view5& v, int* box1, int* box2, int* t1, int*
   return 0;
 }
 
-template <int D>
+template <int D, bool TS>
 static int launch_attn5(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
   using Cfg = Attn5Cfg<D>;
   int kb1, kb2, kt1, ktiles, klast;
@@ -1452,11 +1469,11 @@ static int launch_attn5(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
   if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
   static bool attr_set = false;
   if (!attr_set) {
-    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn5_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn5_tc_kernel<D, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   grid.x = (grid.x + 1) / 2;
-  attn5_tc_kernel<D><<<grid, 640, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  attn5_tc_kernel<D, TS><<<grid, 640, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
@@ -1484,6 +1501,7 @@ static int launch_attn4(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
 
 static unsigned long long* g_attn_dbg = nullptr;
 static int g_attn_early = 1;
+static int g_attn_ts = 1;      // head-dim-40 kernel: probabilities through tensor memory (TS-mode P V product)
 
 }  // namespace a3d
 
@@ -1592,7 +1610,7 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   if (batches > 65535 || a->heads > 65535) return fail(A3D_EINVAL, "a3d_attention: grid too large");
   switch (d) {
     case 40:
-      return launch_attn5<40>(dev, a, mq, grid, st);
+      return g_attn_ts ? launch_attn5<40, true>(dev, a, mq, grid, st) : launch_attn5<40, false>(dev, a, mq, grid, st);
     case 80:
       return launch_attn4<80, 0>(dev, a, mq, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
@@ -1607,7 +1625,8 @@ extern "C" int a3d_debug_set_attn_trace(void* device_counter_u64) {   // buffer 
 }
 
 // tuning hook (tools/attn_timeline.py): 0 switches the one-step-ahead non-blocking barrier tests of the head-dim-40 kernel off
-extern "C" int a3d_debug_set_attn_poly(int early_tests) {
-  a3d::g_attn_early = early_tests ? 1 : 0;
+extern "C" int a3d_debug_set_attn_poly(int flags) {   // bit 0: early barrier tests, bit 1: P through tensor memory (TS-mode P V)
+  a3d::g_attn_early = flags & 1;
+  a3d::g_attn_ts = (flags >> 1) & 1;
   return A3D_OK;
 }

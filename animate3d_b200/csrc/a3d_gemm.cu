@@ -218,9 +218,13 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
       const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && tcount < 60;
       if (tr) p.trace[tcount * 16 + 0] = clock64();
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      if (tr) p.trace[tcount * 16 + 1] = clock64();
-      tc_fence_after();
+      // everything that does not read the accumulator (bias / row-bias staging, the residual tile) is started BEFORE the wait
+      // for the tile's MMAs, so its latency hides behind them
+      auto wait_acc = [&]() {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        if (tr) p.trace[tcount * 16 + 1] = clock64();
+        tc_fence_after();
+      };
       const int64_t row0 = (int64_t)mt * kBM + quad * 32;
       const int64_t row = row0 + lane;
       const bool row_ok = row < p.M;
@@ -352,11 +356,19 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         if (p.R1) ld_global_256(p.R1 + row * p.ldr1 + ocol, r1);
         if (p.R2) ld_global_256(p.R2 + orow * p.ldr2 + ocol, r2);
       };
+      auto load_one = [&](const __half* src, int64_t ld, int64_t r, uint32_t* dst, int64_t ocol) {   // 16 columns of one residual
+        if (ocol + 16 > n_out) {
+          for (int i = 0; i < 16; ++i) reinterpret_cast<__half*>(dst)[i] = ocol + i < n_out ? src[r * ld + ocol + i] : __float2half(0.f);
+        } else {
+          ld_global_256(src + r * ld + ocol, dst);
+        }
+      };
 
       if constexpr (EPI == kEpiF32) {
         // fp32 output (time-embedding table only)
         constexpr int U = BN / 32;
         const int u0 = half ? (U + 1) / 2 : 0, u1 = half ? U : (U + 1) / 2;
+        wait_acc();
 #pragma unroll 1
         for (int ch = u0; ch < u1; ++ch) {
           uint32_t r[32];
@@ -436,22 +448,63 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
         };
-        uint32_t ra[kR ? 16 : 32], rb[kR ? 16 : 32];
-        uint32_t r1a[kR ? 8 : 1], r2a[kR ? 8 : 1], r1b[kR ? 8 : 1], r2b[kR ? 8 : 1];
-        if (u0 < u1) issue(ra, r1a, r2a, u0);
+        if constexpr (kR) {
+          // Residual epilogue: ALL residual (R2) columns this thread will add are requested before the accumulator wait -- they
+          // do not depend on the MMAs, and with one 256-bit load in flight per 16-column unit the K = 320 / 640 projections
+          // (+ residual) spent their epilogue on a chain of exposed L2 / HBM latencies (one per unit).
+          constexpr int UH = (U + 1) / 2;
+          uint32_t r2all[UH][8];
+          const bool pre = p.R2 != nullptr && row_ok;
+          if (pre) {
+#pragma unroll
+            for (int k = 0; k < UH; ++k) {
+              const int u = u0 + k;
+              if (u < u1 && acc_col(u) < p.N) load_one(p.R2, p.ldr2, orow, r2all[k], acc_col(u));
+              // (R1 -- unused by the model since the output GEMMs were merged -- stays on the per-unit path below)
+            }
+          }
+          wait_acc();
+          uint32_t ra[16], rb[16];
+          uint32_t r1a[8], r1b[8], r2d[8];
+          auto issue_r = [&](uint32_t* r, uint32_t* r1, int u) {
+            tmem_ld16p(taddr + u * 16, r);
+            if (p.R1 && row_ok && acc_col(u) < p.N) load_one(p.R1, p.ldr1, row, r1, acc_col(u));
+          };
+          if (u0 < u1) issue_r(ra, r1a, u0);
+#pragma unroll
+          for (int k = 0; k < UH; ++k) {
+            const int u = u0 + k;
+            if (u < u1) {
+              uint32_t* cur = (k & 1) ? rb : ra;
+              uint32_t* nxt = (k & 1) ? ra : rb;
+              uint32_t* cur1 = (k & 1) ? r1b : r1a;
+              uint32_t* nxt1 = (k & 1) ? r1a : r1b;
+              tmem_wait_ld();
+              if (u + 1 < u1) issue_r(nxt, nxt1, u + 1);
+              group_begin(u);
+              process(cur, cur1, pre ? r2all[k] : r2d, u);
+              group_done(u);
+            }
+          }
+        } else {
+          wait_acc();
+          uint32_t ra[32], rb[32];
+          uint32_t r1a[1], r2a[1], r1b[1], r2b[1];
+          if (u0 < u1) issue(ra, r1a, r2a, u0);
 #pragma unroll 1
-        for (int u = u0; u < u1; u += 2) {
-          tmem_wait_ld();
-          if (u + 1 < u1) issue(rb, r1b, r2b, u + 1);
-          group_begin(u);
-          process(ra, r1a, r2a, u);
-          group_done(u);
-          if (u + 1 < u1) {
+          for (int u = u0; u < u1; u += 2) {
             tmem_wait_ld();
-            if (u + 2 < u1) issue(ra, r1a, r2a, u + 2);
-            group_begin(u + 1);
-            process(rb, r1b, r2b, u + 1);
-            group_done(u + 1);
+            if (u + 1 < u1) issue(rb, r1b, r2b, u + 1);
+            group_begin(u);
+            process(ra, r1a, r2a, u);
+            group_done(u);
+            if (u + 1 < u1) {
+              tmem_wait_ld();
+              if (u + 2 < u1) issue(ra, r1a, r2a, u + 2);
+              group_begin(u + 1);
+              process(rb, r1b, r2b, u + 1);
+              group_done(u + 1);
+            }
           }
         }
       }

@@ -42,17 +42,18 @@ WORKER = textwrap.dedent(r'''
     # ---- (1) views span ranks, graph-captured, overlapped gathers
     mine = torch.arange(B, device=dev) * V + rank
     m = MVUNetMotionModel(UNetConfig(num_views=1, num_frames=F), device=dev, view_group=dist.group.WORLD)
-    m.share_packed_weights(full) if False else m.load_state_dict(sd)
+    m.use_cuda_graph = os.environ.get("A3D_SHARDED_GRAPH", "1") == "1"
+    m.load_state_dict(sd)
     outs = [m(sample[mine], 500, text[mine], camera=cam[mine], added_cond_kwargs={"image_embeds": img[mine]}, num_views=1).sample
             for _ in range(3)]
-    assert m._graphs, "sharded forward was not captured in a CUDA graph"
+    assert bool(m._graphs) == m.use_cuda_graph, "sharded forward graph capture state"
     assert m.collectives > 0 and m.collective_bytes > 0
     for o in outs:
         rel = ((o - ref[mine]).norm() / ref[mine].norm()).item()
         assert rel < 5e-3, ("view-sharded", rel)      # two fp16 runs with different tile orders: fp16 noise floor
     assert torch.equal(outs[1], outs[2])
     if rank == 0:
-        print(f"VIEW_SHARDED_OK rel {rel:.2e} collectives {m.collectives} bytes {m.collective_bytes}")
+        print(f"VIEW_SHARDED_OK rel {rel:.2e} collectives {m.collectives} bytes {m.collective_bytes} graph {m.use_cuda_graph}", flush=True)
 
     # ---- (2) CFG branches on two ranks (world 2): sharded step == whole step
     if world == 2:
@@ -109,7 +110,7 @@ def test_view_cfg_and_camera_sharding_over_nccl(tmp_path):
     script.write_text(WORKER)
     env = dict(os.environ, A3D_ROOT=ROOT)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29551", str(script)], env=env, capture_output=True, text=True, timeout=900)
+                        "--master-port", "29551", str(script)], env=env, capture_output=True, text=True, timeout=420)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-6000:]
     for tag in ("VIEW_SHARDED_OK", "CFG_SHARDED_OK", "RASTER_SHARDED_OK"):

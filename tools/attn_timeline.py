@@ -12,12 +12,13 @@ from animate3d_b200 import _lib as L
 from tools import kernel_bench as kb
 
 lib = L.load()
-early = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-L.check(lib.a3d_debug_set_attn_poly(early))
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 3        # bit 0: early barrier tests, bit 1: TS-mode P V
+early = flags
+L.check(lib.a3d_debug_set_attn_poly(flags))
 buf = torch.zeros(8 + 4 * 32 * 8, dtype=torch.int64, device="cuda")
 kb.attn_case("warm", 2, 4, 16, 1024, 40)
 lib.a3d_debug_set_attn_trace(C.c_void_p(buf.data_ptr()))
-kb.attn_case(f"l0 cross-view early_tests={early} (traced)", 2, 4, 16, 1024, 40)
+kb.attn_case(f"l0 cross-view flags={early} (traced)", 2, 4, 16, 1024, 40)
 lib.a3d_debug_set_attn_trace(C.c_void_p(None))
 t = buf[8:].cpu().view(4, 32, 8)
 t0 = int(t[:, 0, 0].min())
@@ -35,4 +36,4 @@ ph = {"wait+ldtm": (0, 1), "p_free": (1, 2), "exp": (2, 3), "publish": (3, 4)}
 for k, (a, b) in ph.items():
     v = (t[:, 8:32, b] - t[:, 8:32, a]).float()
     print(f"{k:14s} mean {v.mean():7.0f}  min {v.min():7.0f}  max {v.max():7.0f}")
-L.check(lib.a3d_debug_set_attn_poly(1))
+L.check(lib.a3d_debug_set_attn_poly(3))
