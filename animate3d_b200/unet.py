@@ -130,7 +130,10 @@ class MVUNetMotionModel(torch.nn.Module):
         self._bufs: Dict[str, torch.Tensor] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._static: Dict[tuple, dict] = {}
-        self.use_cuda_graph = True
+        # View-sharded forwards run eagerly: capturing the asynchronous NCCL all-gathers of torch 2.11 / NCCL 2.28 in a CUDA graph
+        # deadlocks on this stack (measured on 2 x B200: profiles/r02_multi_gpu_2.log); the kernels between two gathers are long
+        # enough for the launch stream to stay ahead.
+        self.use_cuda_graph = view_group is None
         self.gemm_impl = L.IMPL_AUTO
         self.attn_impl = L.IMPL_AUTO
         self.launches = 0            # kernel launches issued by the last eager run (bench's gpu_launches claim)

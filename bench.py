@@ -530,10 +530,17 @@ def run_native(args, rank, world, local_rank):
     d2h = out_h.numel() * out_h.element_size()
 
     peak_tf, peak_hbm, peak_src = peaks()
-    sharded = view_sharded_bench(torch, args, rank, world, local_rank, model, timesteps) if world > 1 else None
     del lat_h, pe_h, cam_h, ie_h, ff_h, out_h
     splat = splat_bench(torch, rank, world, peak_hbm, float((clocks or {}).get("sm_mhz") or 1965.0))
     if rank != 0:
+        # the one-prompt-over-all-ranks mode runs LAST, under a watchdog: a wedged collective must not cost the bench line
+        guard = _Watchdog(180.0, None)
+        if world > 1:
+            try:
+                view_sharded_bench(torch, args, rank, world, local_rank, model, timesteps)
+            except Exception:
+                pass
+        guard.cancel()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -574,15 +581,45 @@ def run_native(args, rank, world, local_rank):
                              "(tensor-only bound would be 0.31 ms); logits here are randn, the in-step kernel time agrees within 2 %"},
         "roofline_gemm": gemm_rf,
         "splat": splat,
-        "view_sharded": sharded,
+        "view_sharded": None,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": (model.launches_per_forward + 1) * args.steps,
         "clocks": clocks,
     }
-    print(json.dumps(out))
+    if world > 1:
+        # strong-scaling mode last, under a watchdog that prints the line without it if a collective wedges
+        fallback = dict(out)
+        fallback["view_sharded"] = {"error": "timed out after 180 s (collective did not complete); not measured in this run"}
+        guard = _Watchdog(180.0, json.dumps(fallback))
+        try:
+            out["view_sharded"] = view_sharded_bench(torch, args, rank, world, local_rank, model, timesteps)
+        except Exception as e:                     # noqa: BLE001 -- a diagnostic mode must not cost the headline line
+            out["view_sharded"] = {"error": f"{type(e).__name__}: {e}"}
+        guard.cancel()
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+class _Watchdog:
+    """If not cancelled within `seconds`: print `line` (rank 0's complete JSON line without the wedged section) and leave the
+    process with exit code 0 -- an in-flight NCCL call cannot be interrupted from Python."""
+
+    def __init__(self, seconds, line):
+        import threading
+        self._t = threading.Timer(seconds, self._fire, args=(line,))
+        self._t.daemon = True
+        self._t.start()
+
+    @staticmethod
+    def _fire(line):
+        if line is not None:
+            print(line, flush=True)
+        os._exit(0)
+
+    def cancel(self):
+        self._t.cancel()
 
 
 def main():
