@@ -965,10 +965,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         }
         const uint32_t sPg = sP_u32 + b * Cfg::kPBox;
         if (j >= 2 && !(p.early_test && p_ok)) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);   // P columns of step j-2 consumed
-        if (p.early_test) {   // tests for step j+1, consumed at its top
-          s_ok = j + 1 < n && (TS ? mbar_test(&s_full[2 * g], (j + 1) & 1) : mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1));
-          p_ok = j + 1 < 2 || mbar_test(&my_pv_done[(j + 1) & 1], ((j - 1) >> 1) & 1);
-        }
+
         if (tr) trow[2] = clock64();
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
@@ -1015,6 +1012,11 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           }
           tmem_wait_st();
           m_run = m_up;
+        }
+        if (p.early_test) {   // tests for step j+1, consumed at its top.  Issued AFTER the exponentials: QK^T(j+1) (TS: started when this
+                              // step freed S) and P V(j-1) (started when step j-1 published) have had the whole phase to complete
+          s_ok = j + 1 < n && (TS ? mbar_test(&s_full[2 * g], (j + 1) & 1) : mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1));
+          p_ok = j + 1 < 2 || mbar_test(&my_pv_done[(j + 1) & 1], ((j - 1) >> 1) & 1);
         }
         if (tr) trow[3] = clock64();
         if (TS) tmem_wait_st(); else fence_proxy_async_smem();

@@ -23,6 +23,8 @@ JSON line keys beyond the base contract:
                (50k gaussians, 4 views x 16 timestamps = 64 cameras at 512^2), forward and forward+backward, with per-stage
                times from CUDA events inside liba3d.so and the stage rooflines of SURVEY 8(d); for N > 1 the cameras are
                sharded r::N and the deformation-field gradients all-reduced (one flat bucket)
+  sds_step     (N = 1) one whole 4D-SDS refine step of BASELINE configs[2] on the engine: render -> VAE encoder (with grad) -> CFG
+               UNet -> loss -> backward to the deformation field
   view_sharded (N > 1) ONE prompt spread over the N ranks -- CFG branches over 2 ranks and / or the 4 views over 4 ranks with
                the cross-view K|V all-gather over NCCL -- as a strong-scaling number next to the weak-scaling `value`, with the
                exposed communication time (same forward with the collectives skipped)
@@ -361,6 +363,61 @@ def splat_bench(torch, rank, world, peak_hbm, sm_mhz, iters=5):
     return out
 
 
+def sds_step_bench(torch, unet, iters=3):
+    """BASELINE configs[2] end to end: ONE 4D-SDS refine step on the engine -- 64 cameras (4 views x 16 timestamps) of 50k deformed
+    gaussians rendered at 512^2, resized to 256^2, VAE-encoded WITH grad, one CFG UNet evaluation (no grad), x0-reconstruction
+    loss, backward through the VAE encoder, the rasterizer and the deformation field (systems/animate3d.py:180-215;
+    animatemv_guidance.py:515-600).  Random-init VAE / UNet weights, seeded synthetic scene."""
+    from animate3d_b200.guidance import AnimateMVDiffusionGuidance, PrecomputedPromptUtils
+    from animate3d_b200.renderer import make_renderer
+    from animate3d_b200.vae import AutoencoderKL, vae_key_plan
+    from tools.splat_bench import cameras, synthetic_model
+    dev = unet.device
+    g = torch.Generator(device=dev).manual_seed(7)
+    vae = AutoencoderKL(device=dev)
+    sd = {}
+    for k, shape in vae_key_plan(vae.config).items():
+        if "norm" in k.split(".")[-2]:
+            sd[k] = torch.ones(shape, device=dev) if k.endswith("weight") else torch.zeros(shape, device=dev)
+        elif k.endswith("bias"):
+            sd[k] = torch.zeros(shape, device=dev)
+        else:
+            fan = 1
+            for s_ in shape[1:]:
+                fan *= s_
+            sd[k] = torch.randn(shape, device=dev, generator=g) * fan ** -0.5
+    vae.load_state_dict(sd)
+    del sd
+    model = synthetic_model(50000, device=dev)
+    rend = make_renderer(model).train()
+    c2w, fovy, ts = cameras(device=dev)
+    batch = {"c2w": c2w, "fovy": fovy, "width": 512, "height": 512, "timestamps": ts, "do_guidance": True, "do_reconstruction": True}
+    guide = AnimateMVDiffusionGuidance({"n_view": NV, "n_frame": NF, "guidance_scale": 5.0, "recon_std_rescale": 0.5,
+                                        "min_step_percent": 0.02, "max_step_percent": 0.2}, unet=unet, vae=vae)
+    guide.update_step(0, 0)
+    pu = PrecomputedPromptUtils(torch.randn(77, 768, device=dev, generator=g), torch.randn(77, 768, device=dev, generator=g))
+    img = torch.randn(NV, 1024, device=dev, generator=g)
+    z = torch.zeros(NV * NF, device=dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def step():
+        for p_ in params:
+            p_.grad = None
+        out = rend.batch_forward(batch)
+        go = guide(out["comp_rgb"], pu, z, z, z, c2w, image_embeds=img)
+        go["loss_sds"].backward()
+        return go["loss_sds"]
+
+    loss = step()
+    step()
+    ms = _time_cuda(torch, step, iters=iters, warm=0)
+    gn = float(sum(p_.grad.float().pow(2).sum() for p_ in params if p_.grad is not None).sqrt())
+    return {"ms_per_step": ms, "steps_per_s": 1000.0 / ms, "loss": float(loss.detach()), "grad_norm_deformation_field": gn,
+            "workload": "render 64 x 512^2 (50k gaussians, deformation field) -> 256^2 -> VAE encoder fwd+bwd (64 images) -> CFG UNet "
+                        "(2 x 4 views x 16 frames) -> x0-recon loss -> rasterizer + deformation backward",
+            "finite": bool(loss.isfinite()) and gn == gn}
+
+
 def view_sharded_bench(torch, args, rank, world, local_rank, base_model, timesteps):
     """ONE prompt over all ranks (SURVEY 8e / BASELINE configs[3]): world 2 = the two CFG branches; world 4 = the 4 views (K|V
     all-gather per cross-view attention); world 8 = both.  Returns steps/s of that single prompt, the exposed communication
@@ -552,6 +609,12 @@ def run_native(args, rank, world, local_rank):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("attn_l0_dram_bytes_per_launch")     # ncu dram__bytes_read+write per launch (r01 capture)
     gemm_rf = gemm_rooflines(torch, peak_tf, peak_hbm)
+    sds = None
+    if world == 1:
+        try:
+            sds = sds_step_bench(torch, model)
+        except Exception as e:                     # noqa: BLE001 -- an extra, must not cost the headline line
+            sds = {"error": f"{type(e).__name__}: {e}"}
     cpu = None
     if world == 1:
         times, fl, cores = cpu_oracle_sample(1)
@@ -581,6 +644,7 @@ def run_native(args, rank, world, local_rank):
                              "(tensor-only bound would be 0.31 ms); logits here are randn, the in-step kernel time agrees within 2 %"},
         "roofline_gemm": gemm_rf,
         "splat": splat,
+        "sds_step": sds,
         "view_sharded": None,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
