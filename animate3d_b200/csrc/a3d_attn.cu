@@ -31,6 +31,7 @@ struct AttnDev {
   int accumulate;
   float out_scale;
   int early_test;            // head-dim-40 kernel: non-blocking barrier tests one step ahead (see the step loop)
+  int late_pfree;            // head-dim-40 kernel, TS: test "P buffer consumed" after the exponentials instead of before them
   unsigned long long* dbg;   // debug (null in production): dbg[0] counts (warp, step) pairs that took the lazy-rescale branch;
                              // dbg[8 + (w*32 + j)*8 + k]: clock64 timeline of 4 softmax warps of CTA (0,0,0) (head-dim-40 kernel)
 };
@@ -704,24 +705,31 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
 //   partial results of a row are merged once, in the epilogue: O = (w0 O0 + w1 O1) / (w0 l0 + w1 l1), w_h = 2^(m_h - m).
 //   TMEM: S[g][b] at column (2g+b)*64, O[g][h] at 256 + (2g+h)*64.
 // ---------------------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int G>
 struct Attn5Cfg {
   static constexpr int kDqk = (D + 15) / 16 * 16;
   static constexpr int kDv = (D + 1 + 15) / 16 * 16;
   static constexpr int kQB = (kDqk + 63) / 64;       // 64-column boxes per Q / K row
   static constexpr int kVB = (kDv + 63) / 64;
-  static constexpr int kStages = (kQB == 1) ? 4 : 2;
+  static constexpr int kStages = (G == 2) ? 4 : 3;       // G = 1: two CTAs share an SM's shared memory
   static constexpr int kQBox = 128 * 128;            // 128 rows x 64 cols fp16
   static constexpr int kKVBox = 64 * 128;            // 64 keys x 64 cols fp16
-  static constexpr int kSmemQ = 2 * kQB * kQBox;
+  static constexpr int kSmemQ = G * kQB * kQBox;
   static constexpr int kSmemK = kStages * kQB * kKVBox;
   static constexpr int kSmemV = kStages * kVB * kKVBox;
   static constexpr int kPBox = 128 * 128;            // 128 rows x 64 keys fp16
-  static constexpr int kSmemP = 2 * 2 * kPBox;       // [2 tiles][2 buffers]
-  static constexpr int kSmemMx = 2 * 2 * 128 * 4;       // [tile][half][row] final stabilisers (epilogue merge)
+  static constexpr int kSmemP = G * 2 * kPBox;       // [G tiles][2 buffers]
+  static constexpr int kSmemMx = G * 2 * 128 * 4;       // [tile][half][row] final stabilisers (epilogue merge)
   static constexpr int kSmemBytes = kSmemQ + kSmemK + kSmemV + kSmemP + kSmemMx + 1024 + 512;
   static_assert(kDv <= 64 && kQB == 1 && kVB == 1, "v5 keeps four O accumulators in TMEM: head_dim <= 47 only");
-  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kSmemBytes <= (G == 2 ? 227 : 113) * 1024, "shared memory budget");
+  static constexpr int kThreads = G == 2 ? 640 : 320;
+  static constexpr int kSoft = 8 * G;                        // softmax warps [0, 8G); MMA issuers kSoft .. kSoft+G-1
+  static constexpr int kTmaWarp = kSoft + G;                 // TMA producer (also initialises the barriers)
+  static constexpr int kAllocWarp = G == 2 ? 19 : kTmaWarp;  // TMEM allocation / release
+  static constexpr int kTmemCols = G == 2 ? 512 : 256;
+  static constexpr int kColP = G == 2 ? 128 : 64;            // TS: P[g][b] at kColP + (2g+b)*32
+  static constexpr int kColO = G == 2 ? 256 : 128;           // O[g][h] at kColO + (2g+h)*64
   static constexpr int kOChunks = kDv / 16;                  // 16-column chunks of an O row
   static constexpr int kOChunks0 = (kOChunks + 1) / 2;       // chunks half 0 owns (rescale + epilogue); half 1: the rest
 };
@@ -731,11 +739,11 @@ struct Attn5Cfg {
 //   (tcgen05.mma [d], [a_tmem], b_desc): no swizzled shared-memory stores, no fence.proxy.async / MEMBAR per step.  TMEM then holds
 //   S[g] single-buffered at column g*64 (S(j) sits in registers right after the step starts, so QK^T(j+1) has a whole step to
 //   land), P[g][b] (64 keys = 32 packed columns) at 128 + (2g+b)*32, O[g][h] at 256 + (2g+h)*64.
-template <int D, bool TS>
-__global__ void __launch_bounds__(640, 1)
+template <int D, bool TS, int G>
+__global__ void __launch_bounds__(G == 2 ? 640 : 320, G == 2 ? 1 : 2)
 attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV) {
-  using Cfg = Attn5Cfg<D>;
+  using Cfg = Attn5Cfg<D, G>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -759,20 +767,34 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt0 = blockIdx.x * 2;
-  const bool has1 = qt0 + 1 < p.q_tiles;
+  const int qt0 = blockIdx.x * G;
+  const bool has1 = G == 2 && qt0 + 1 < p.q_tiles;
   const int head = blockIdx.y;
   const int qb = blockIdx.z;
   const int n = p.kv_tiles;
+  // debug: life cycle of four CTAs (linear ids 0, 1/4, 1/2, 3/4 of the grid): clock64 at entry / set-up done / first scores in
+  // registers / step loop done / accumulators complete / rows stored / exit, and the SM id (tools/attn_timeline.py)
+  unsigned long long* ctr = nullptr;
+  if (p.dbg) {
+    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z), tot = gridDim.x * gridDim.y * gridDim.z;
+    for (unsigned k = 0; k < 4; ++k)
+      if (lin == (tot / 4) * k) ctr = p.dbg + 8 + 4 * 32 * 8 + k * 8;
+  }
+  if (ctr && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    ctr[0] = clock64();
+    ctr[7] = smid;
+  }
 
-  if (p.rows_q < 128 || p.k_box1 * p.k_box2 < 64 || !has1) {
+  if (p.rows_q < 128 || p.k_box1 * p.k_box2 < 64 || (G == 2 && !has1)) {
     // partially filled tiles: rows TMA never writes must read as zeros (0 * garbage could be NaN in P V)
     uint4* z = reinterpret_cast<uint4*>(sQ);
     const int n16 = (Cfg::kSmemQ + Cfg::kSmemK + Cfg::kSmemV) / 16;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
-  if (warp == 18 && lane == 0) {
+  if (warp == Cfg::kTmaWarp && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
@@ -796,15 +818,16 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     mbar_init(&o_full[1], 1);
     mbar_fence_init();
   }
-  if (warp == 19) tmem_alloc<512>(tmem_slot);
+  if (warp == Cfg::kAllocWarp) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (ctr && threadIdx.x == 0) ctr[1] = clock64();
   const int q_i3 = qb % p.q_e3;
   const int q_i4 = qb / p.q_e3;
 
-  if (warp == 18) {
+  if (warp == Cfg::kTmaWarp) {
     if (lane == 0) {
       const int kb = qb / p.kv_div;
       const int k_i3 = p.kv_i3_zero ? 0 : (kb % p.k_e3);
@@ -844,8 +867,8 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         load_v(j);
       }
     }
-  } else if (warp == 16 || warp == 17) {
-    const int g = warp - 16;
+  } else if (warp >= Cfg::kSoft && warp < Cfg::kSoft + G) {
+    const int g = warp - Cfg::kSoft;
     if (lane == 0 && (g == 0 || has1)) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 64, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, Cfg::kDv, false, true);
@@ -854,8 +877,8 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       const uint64_t dk = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t dv = make_smem_desc_sw128(smem_u32(sV), Cfg::kKVBox, 1024);   // MN-major: next 64 columns one box on
       const uint64_t dp = make_smem_desc_sw128(smem_u32(sP + 2 * g * Cfg::kPBox), 16, 1024);
-      const uint32_t tS = tmem_base + (TS ? g * 64 : 2 * g * 64), tO = tmem_base + 256 + 2 * g * 64;
-      const uint32_t tP = tmem_base + 128 + 2 * g * 32;     // TS only
+      const uint32_t tS = tmem_base + (TS ? g * 64 : 2 * g * 64), tO = tmem_base + Cfg::kColO + 2 * g * 64;
+      const uint32_t tP = tmem_base + Cfg::kColP + 2 * g * 32;     // TS only
       auto issue_qk = [&](int j) {      // S[g][j&1] (TS: S[g]) = Q_g K_j^T; the K stage is released as soon as these MMAs retire
         const uint64_t kb_ = dk + (uint64_t)((j % S) * ((Cfg::kQB * Cfg::kKVBox) >> 4));
 #pragma unroll
@@ -907,14 +930,14 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
     } else if (lane == 0 && n > 0) {
       // tile 1 absent: nothing to issue, and k_empty / v_empty were initialised for a single committer
     }
-  } else if (warp < 16) {
+  } else if (warp < Cfg::kSoft) {
     const int g = warp >> 3;
     if (g == 0 || has1) {
       const int h = (warp >> 2) & 1;
       const int quad = warp & 3;
       const int r = quad * 32 + lane;
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-      const uint32_t tmem_O = tmem_base + 256 + (2 * g + h) * 64;     // this half's accumulator
+      const uint32_t tmem_O = tmem_base + Cfg::kColO + (2 * g + h) * 64;     // this half's accumulator
       const int pair_bar = 1 + g * 4 + quad;       // named barrier shared with the warp that owns the other 32 keys
       float m_run = -INFINITY;
       uint64_t* my_p_full = p_full + (2 * g + h) * 2;
@@ -946,6 +969,7 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         tmem_ld32(tmem_base + lane_addr + (TS ? g * 64 : b * 64) + 32 * h, s);
         tmem_wait_ld();
         if (tr) trow[1] = clock64();
+        if (ctr && j == 0 && threadIdx.x == 0) ctr[2] = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[sb_]);   // S buffer may be overwritten by the next QK^T into it
@@ -964,8 +988,15 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           m_run = fmaxf(fmaxf(mx0, mx1) * p.scale_log2, -1.0e30f);
         }
         const uint32_t sPg = sP_u32 + b * Cfg::kPBox;
-        if (j >= 2 && !(p.early_test && p_ok)) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);   // P columns of step j-2 consumed
-
+        // P buffer of step j-2 consumed?  Shared-memory P: needed before the first store of the loop below.  TS: the probabilities
+        // stay in registers until the single tcgen05.st after the loop, so the check moves there (by then P V(j-2) has long retired
+        // and a non-blocking test suffices -- in front of the loop it cost every step ~200-400 cycles of barrier latency)
+        const bool late = TS && p.late_pfree;
+        if (!late && j >= 2 && !(p.early_test && p_ok)) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);
+        if (p.early_test) {   // tests for step j+1, consumed at its top
+          s_ok = j + 1 < n && (TS ? mbar_test(&s_full[2 * g], (j + 1) & 1) : mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1));
+          if (!late) p_ok = j + 1 < 2 || mbar_test(&my_pv_done[(j + 1) & 1], ((j - 1) >> 1) & 1);
+        }
         if (tr) trow[2] = clock64();
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
@@ -991,7 +1022,10 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
             }
             if (!TS) st_shared_v4(sPg + p_off[c16], q);
           }
-          if (TS) tmem_st16(tmem_base + lane_addr + 128 + (uint32_t)(b * 32 + h * 16), pk);
+          if (TS) {
+            if (late && j >= 2 && pass == 0 && !mbar_test(&my_pv_done[j & 1], ((j - 2) >> 1) & 1)) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);
+            tmem_st16(tmem_base + lane_addr + Cfg::kColP + (uint32_t)(b * 32 + h * 16), pk);
+          }
           if (pass > 0 || j == 0) break;
           const float m_new = fmaxf(mx0, mx1) * p.scale_log2;
           if (!__any_sync(0xffffffffu, m_new - m_run > kRescale5)) break;
@@ -1013,11 +1047,6 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
           tmem_wait_st();
           m_run = m_up;
         }
-        if (p.early_test) {   // tests for step j+1, consumed at its top.  Issued AFTER the exponentials: QK^T(j+1) (TS: started when this
-                              // step freed S) and P V(j-1) (started when step j-1 published) have had the whole phase to complete
-          s_ok = j + 1 < n && (TS ? mbar_test(&s_full[2 * g], (j + 1) & 1) : mbar_test(&s_full[2 * g + ((j + 1) & 1)], ((j + 1) >> 1) & 1));
-          p_ok = j + 1 < 2 || mbar_test(&my_pv_done[(j + 1) & 1], ((j - 1) >> 1) & 1);
-        }
         if (tr) trow[3] = clock64();
         if (TS) tmem_wait_st(); else fence_proxy_async_smem();
         tc_fence_before();
@@ -1026,15 +1055,17 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
         if (tr) trow[4] = clock64();
       }
       // ---- epilogue: merge the two halves' partial softmax states; this half writes its chunks of the rows
+      if (ctr && threadIdx.x == 0) ctr[3] = clock64();
       mbar_wait(&o_full[g], 0);
       tc_fence_after();
+      if (ctr && threadIdx.x == 0) ctr[4] = clock64();
       sMx[(g * 2 + h) * 128 + r] = m_run;
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       const float m_oth = sMx[(g * 2 + (h ^ 1)) * 128 + r];
       const float m_all = fmaxf(m_run, m_oth);
       const float w_mine = ex2_approx(m_run - m_all), w_oth = ex2_approx(m_oth - m_all);
       const float w0 = h ? w_oth : w_mine, w1 = h ? w_mine : w_oth;
-      const uint32_t tO0 = tmem_base + 256 + 2 * g * 64 + lane_addr, tO1 = tO0 + 64;
+      const uint32_t tO0 = tmem_base + Cfg::kColO + 2 * g * 64 + lane_addr, tO1 = tO0 + 64;
       float inv;
       {
         uint32_t o0[16], o1[16];
@@ -1085,9 +1116,11 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
       }
     }
   }
+  if (ctr && threadIdx.x == 0) ctr[5] = clock64();
   tc_fence_before();
   __syncthreads();
-  if (warp == 19) tmem_dealloc<512>(tmem_base);
+  if (ctr && threadIdx.x == 0) ctr[6] = clock64();
+  if (warp == Cfg::kAllocWarp) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1459,9 +1492,12 @@ static int tile_geom_k64(const a3d_view5& v, int* box1, int* box2, int* t1, int*
   return 0;
 }
 
-template <int D, bool TS>
+static int g_attn_g1 = 1;      // head-dim-40 kernel: one 128-query tile per CTA, two CTAs per SM (prologue / epilogue of one overlaps the other)
+static int g_attn_late_pfree = 1;
+
+template <int D, bool TS, int G>
 static int launch_attn5(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* mq, dim3 grid, cudaStream_t st) {
-  using Cfg = Attn5Cfg<D>;
+  using Cfg = Attn5Cfg<D, G>;
   int kb1, kb2, kt1, ktiles, klast;
   if (int r = tile_geom_k64(a->k, &kb1, &kb2, &kt1, &ktiles, &klast)) return r;
   dev.kv_tiles = ktiles; dev.rows_k = klast; dev.k_t1 = kt1; dev.k_box1 = kb1; dev.k_box2 = kb2;
@@ -1471,11 +1507,11 @@ static int launch_attn5(AttnDev dev, const a3d_attn_args* a, const CUtensorMap* 
   if (int r = view_map(a->v, kb1, kb2, &mv)) return r;
   static bool attr_set = false;
   if (!attr_set) {
-    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn5_tc_kernel<D, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    A3D_CUDA_CHECK(cudaFuncSetAttribute(attn5_tc_kernel<D, TS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  grid.x = (grid.x + 1) / 2;
-  attn5_tc_kernel<D, TS><<<grid, 640, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
+  if (G == 2) grid.x = (grid.x + 1) / 2;
+  attn5_tc_kernel<D, TS, G><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(dev, *mq, *mk, *mv);
   A3D_LAUNCH_CHECK();
   return A3D_OK;
 }
@@ -1599,6 +1635,7 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   dev.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
   dev.dbg = g_attn_dbg;
   dev.early_test = g_attn_early;
+  dev.late_pfree = g_attn_late_pfree;
   if ((a->os1 | a->os2 | a->os3 | a->os4) % 8 || (reinterpret_cast<uintptr_t>(a->out) & 15))
     return fail(A3D_EINVAL, "a3d_attention: output rows must be 16-byte aligned");
   const CUtensorMap *mq, *mk, *mv;
@@ -1612,7 +1649,8 @@ extern "C" int a3d_attention(const a3d_attn_args* a, void* stream) {
   if (batches > 65535 || a->heads > 65535) return fail(A3D_EINVAL, "a3d_attention: grid too large");
   switch (d) {
     case 40:
-      return g_attn_ts ? launch_attn5<40, true>(dev, a, mq, grid, st) : launch_attn5<40, false>(dev, a, mq, grid, st);
+      if (g_attn_g1) return g_attn_ts ? launch_attn5<40, true, 1>(dev, a, mq, grid, st) : launch_attn5<40, false, 1>(dev, a, mq, grid, st);
+      return g_attn_ts ? launch_attn5<40, true, 2>(dev, a, mq, grid, st) : launch_attn5<40, false, 2>(dev, a, mq, grid, st);
     case 80:
       return launch_attn4<80, 0>(dev, a, mq, grid, st);
     default: return launch_attn<160>(dev, mq, mk, mv, grid, st);
@@ -1630,5 +1668,7 @@ extern "C" int a3d_debug_set_attn_trace(void* device_counter_u64) {   // buffer 
 extern "C" int a3d_debug_set_attn_poly(int flags) {   // bit 0: early barrier tests, bit 1: P through tensor memory (TS-mode P V)
   a3d::g_attn_early = flags & 1;
   a3d::g_attn_ts = (flags >> 1) & 1;
+  a3d::g_attn_g1 = (flags >> 2) & 1;
+  a3d::g_attn_late_pfree = (flags >> 3) & 1;
   return A3D_OK;
 }

@@ -47,17 +47,21 @@ struct GemmDev {
 };
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below fp16 output
-// resolution): 1 rcp + 1 ex2 on the XU pipe + 8 FMA instead of erff's ~30 instructions (the GEGLU epilogue is ALU-bound)
+// resolution): 1 rcp + 1 ex2 on the XU pipe + 11 FMA-pipe instructions instead of erff's ~30 (the GEGLU epilogue is ALU-bound)
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  // gelu(x) = x/2 + |x|/2 erf(|x| / sqrt 2);  erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1 / (1 + 0.3275911 z).  Constants folded so
+  // that one evaluation is 7 FFMA + 4 FMUL + MUFU.RCP + MUFU.EX2 (the K = 320 GEGLU tiles are bound by epilogue instruction issue)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = ex2_approx(-z * z * 1.4426950408889634f);
-  const float erf_abs = 1.0f - poly * t * e;
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float xs = x * 0.84932180028801904f;              // sqrt(log2(e) / 2): exp(-x^2 / 2) = 2^(-xs^2)
+  const float e = ex2_approx(-xs * xs);
+  const float erf_abs = fmaf(-(poly * t), e, 1.0f);
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), erf_abs, h);
 }
 
 __device__ __forceinline__ int64_t perm_row(int64_t m, int64_t a, int64_t b) {
@@ -214,6 +218,30 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
     int acc = 0;
     uint32_t acc_phase = 0;
     int tcount = 0;
+    // row-bias table rows of a tile are FETCHED one tile ahead into registers (their global-load latency then hides behind the
+    // previous tile's epilogue instead of standing in front of this one) and only copied to shared memory at the tile's top
+    constexpr int kRbVec = BN / 4;
+    constexpr int kRbPf = (16 * kRbVec + 255) / 256;      // float4 per thread for <= 16 staged rows
+    float4 rb_pf[kRbPf];
+    auto rb_fetch = [&](int t) {
+      const int64_t tile_row0 = (int64_t)(t / p.tiles_n) * kBM;
+      const int ntf = t % p.tiles_n;
+#pragma unroll
+      for (int k = 0; k < kRbPf; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        rb_pf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < p.rb_slots * kRbVec) {
+          const int slot = i / kRbVec, c4 = i % kRbVec;
+          const int64_t rep = tile_row0 + (p.rb_stage == 1 ? (int64_t)slot * p.rb_div : (int64_t)slot);
+          const int64_t trow = (rep / p.rb_div) % p.rb_mod;
+          const int64_t col = (int64_t)ntf * BN + c4 * 4;
+          if (col + 4 <= p.N && rep < p.M) rb_pf[k] = __ldg(reinterpret_cast<const float4*>(p.rowbias + trow * p.rb_ld + col));
+        }
+      }
+    };
+    constexpr bool kRbAhead = EPI == kEpiPlain;      // (the residual epilogue has no registers to spare; it fetches in place)
+    constexpr bool rb_ahead = kRbAhead;
+    if (rb_ahead && p.rb_stage && (int)blockIdx.x < num_tiles) rb_fetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / p.tiles_n, nt = tile % p.tiles_n;
       const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && tcount < 60;
@@ -231,6 +259,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       const int64_t rbrow = (p.rowbias && row_ok) ? ((row / p.rb_div) % p.rb_mod) : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const int64_t n_out = (EPI == kEpiGeglu) ? p.N / 2 : p.N;
+      const bool tile_full = (int64_t)(nt + 1) * BN <= p.N;       // no ragged columns in this tile: the per-unit bounds tests fold away
       // the tile's BN bias values: one coalesced load by the 256 epilogue threads, then broadcast reads from shared memory
       float* sb = reinterpret_cast<float*>(smem_stage) + acc * 256;
       // Row-bias (positional-encoding / time-embedding tables, fp32 [table rows, N]): a 128-row tile touches at most 16
@@ -240,17 +269,13 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       const float* rbs = nullptr;
       if (p.rb_stage) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int64_t tile_row0 = (int64_t)mt * kBM;
-        constexpr int kVec = BN / 4;
-        for (int i = threadIdx.x; i < p.rb_slots * kVec; i += 256) {
-          const int slot = i / kVec, c4 = i % kVec;
-          const int64_t rep = tile_row0 + (p.rb_stage == 1 ? (int64_t)slot * p.rb_div : (int64_t)slot);
-          const int64_t trow = (rep / p.rb_div) % p.rb_mod;
-          const int64_t col = (int64_t)nt * BN + c4 * 4;
-          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col + 4 <= p.N && rep < p.M) v4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + trow * p.rb_ld + col));
-          *reinterpret_cast<float4*>(smem_rb + slot * Cfg::kRbLd + c4 * 4) = v4;
+        if (!rb_ahead) rb_fetch(tile);
+#pragma unroll
+        for (int k = 0; k < kRbPf; ++k) {
+          const int i = threadIdx.x + 256 * k;
+          if (i < p.rb_slots * kRbVec) *reinterpret_cast<float4*>(smem_rb + (i / kRbVec) * Cfg::kRbLd + (i % kRbVec) * 4) = rb_pf[k];
         }
+        if (rb_ahead && tile + (int)gridDim.x < num_tiles) rb_fetch(tile + gridDim.x);
         const int rit = quad * 32 + lane;
         const int slot = p.rb_stage == 1 ? (int)(rit / p.rb_div) : (int)(rit % p.rb_mod);
         rbs = smem_rb + slot * Cfg::kRbLd;
@@ -265,7 +290,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       // fp32 values of NC (16 or 32) consecutive accumulator columns -> + bias + rowbias, * scale
       auto finish = [&](float* v, int64_t col0, auto nc_tag) {
         constexpr int NC = decltype(nc_tag)::value;
-        if (col0 + NC <= p.N) {
+        if (tile_full || col0 + NC <= p.N) {
           if (p.bias) {
             const float4* bs = reinterpret_cast<const float4*>(sb + (col0 - (int64_t)nt * BN));
 #pragma unroll
@@ -336,7 +361,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           return;
         }
         __half* o = reinterpret_cast<__half*>(p.C) + orow * p.ldc + ocol;
-        if (ocol + NC <= n_out) {
+        if (tile_full || ocol + NC <= n_out) {
 #pragma unroll
           for (int i = 0; i < NC / 16; ++i) st_global_256(o + 16 * i, h + 8 * i);
         } else {
@@ -345,7 +370,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
       };
       // residual tiles: 16 columns (one 256-bit load each) per unit
       auto load_res = [&](uint32_t* r1, uint32_t* r2, int64_t ocol) {
-        if (ocol + 16 > n_out) {   // ragged tail: scalar fill
+        if (!tile_full && ocol + 16 > n_out) {   // ragged tail: scalar fill
           for (int i = 0; i < 16; ++i) {
             const bool ok = ocol + i < n_out;
             if (p.R1) reinterpret_cast<__half*>(r1)[i] = ok ? p.R1[row * p.ldr1 + ocol + i] : __float2half(0.f);
@@ -357,7 +382,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
         if (p.R2) ld_global_256(p.R2 + orow * p.ldr2 + ocol, r2);
       };
       auto load_one = [&](const __half* src, int64_t ld, int64_t r, uint32_t* dst, int64_t ocol) {   // 16 columns of one residual
-        if (ocol + 16 > n_out) {
+        if (!tile_full && ocol + 16 > n_out) {
           for (int i = 0; i < 16; ++i) reinterpret_cast<__half*>(dst)[i] = ocol + i < n_out ? src[r * ld + ocol + i] : __float2half(0.f);
         } else {
           ld_global_256(src + r * ld + ocol, dst);
@@ -402,14 +427,14 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
             tmem_ld16p(taddr + (u >> 1) * 64 + 32 + 16 * (u & 1), r + 16);
           } else if (kR) {
             tmem_ld16p(taddr + u * 16, r);
-            if (row_ok && acc_col(u) < p.N) load_res(r1, r2, acc_col(u));
+            if (row_ok && (tile_full || acc_col(u) < p.N)) load_res(r1, r2, acc_col(u));
           } else {
             tmem_ld32p(taddr + u * 32, r);
           }
         };
         auto process = [&](uint32_t* r, uint32_t* r1, uint32_t* r2, int u) {
           const int64_t col0 = acc_col(u);
-          if (!row_ok || col0 >= p.N) return;
+          if (!row_ok || (!tile_full && col0 >= p.N)) return;
           float* v = reinterpret_cast<float*>(r);
           if (kG) {
             finish(v, col0, N16{});
@@ -437,7 +462,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           const int64_t gcol = cend - 64;
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && gcol < n_out) {
+          if (lane == 0 && (tile_full || gcol < n_out)) {
             tma_store_5d(&mapC, smem_out + (warp & 7) * 4096, (int)gcol, (int)row0, 0, 0, 0);
             tma_store_commit();
           }
@@ -459,7 +484,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
 #pragma unroll
             for (int k = 0; k < UH; ++k) {
               const int u = u0 + k;
-              if (u < u1 && acc_col(u) < p.N) load_one(p.R2, p.ldr2, orow, r2all[k], acc_col(u));
+              if (u < u1 && (tile_full || acc_col(u) < p.N)) load_one(p.R2, p.ldr2, orow, r2all[k], acc_col(u));
               // (R1 -- unused by the model since the output GEMMs were merged -- stays on the per-unit path below)
             }
           }
@@ -468,7 +493,7 @@ gemm_tc_kernel(const GemmDev p, const __grid_constant__ CUtensorMap mapA, const 
           uint32_t r1a[8], r1b[8], r2d[8];
           auto issue_r = [&](uint32_t* r, uint32_t* r1, int u) {
             tmem_ld16p(taddr + u * 16, r);
-            if (p.R1 && row_ok && acc_col(u) < p.N) load_one(p.R1, p.ldr1, row, r1, acc_col(u));
+            if (p.R1 && row_ok && (tile_full || acc_col(u) < p.N)) load_one(p.R1, p.ldr1, row, r1, acc_col(u));
           };
           if (u0 < u1) issue_r(ra, r1a, u0);
 #pragma unroll

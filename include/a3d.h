@@ -275,11 +275,13 @@ int a3d_arap(const float* nodes, int Nt, int Nv, const int32_t* nbr, int K, cons
 
 /* debug hook: a device uint64 counter the tcgen05 attention kernels bump once per (warp, key step) that takes the
    lazy-rescale branch of the single-pass softmax (NULL = off; tests use it to prove adversarial inputs reach that branch).
-   The buffer must hold 8 + 4*32*8 uint64: words 8.. receive a clock64 timeline of four softmax warps of CTA (0,0,0) of the
+   The buffer must hold 8 + 4*32*8 + 32 uint64: words 8.. receive a clock64 timeline of four softmax warps of CTA (0,0,0) of the
    head-dim-40 kernel (tools/attn_timeline.py) */
 int a3d_debug_set_attn_trace(void* device_counter_u64);
-/* tuning hook of the head-dim-40 attention kernel: 0 switches its one-step-ahead non-blocking barrier tests off (default on) */
-int a3d_debug_set_attn_poly(int early_tests);
+/* tuning hook of the head-dim-40 attention kernel (default 15 = all on): bit 0 one-step-ahead non-blocking barrier tests, bit 1
+   probabilities through tensor memory (TS-mode P V), bit 2 one 128-query tile per CTA with two CTAs per SM, bit 3 (TS) "P buffer
+   consumed" checked after the exponentials instead of before them */
+int a3d_debug_set_attn_poly(int flags);
 /* measurement hooks of the rasterizer (bench.py's splat roofline): with timing enabled every forward / backward records CUDA
    events at its stage boundaries; a3d_debug_raster_stage_ms returns the milliseconds of the last forward's stages
    [0] preprocess [1] scan + counts + duplicate [2] radix sort [3] tile ranges [4] render and the last backward's [5] render

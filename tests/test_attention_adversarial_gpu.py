@@ -55,7 +55,7 @@ def _run(q, k, v, batches, lq, lk, d, scale):
     vq = ops.view5(qb, 0, ldq, (ldq, lq * ldq, lq * ldq, lq * ldq), (lq, 1, 1, batches))
     vk = ops.view5(kvb, 0, ldk, (ldk, lk * ldk, lk * ldk, lk * ldk), (lk, 1, 1, batches))
     vv = ops.view5(kvb, HEADS * dqk, ldk - HEADS * dqk, (ldk, lk * ldk, lk * ldk, lk * ldk), (lk, 1, 1, batches))
-    counter = torch.zeros(8 + 4 * 32 * 8, dtype=torch.int64, device=DEV)      # [0] = rescale count, [8:] = timeline words
+    counter = torch.zeros(8 + 4 * 32 * 8 + 32, dtype=torch.int64, device=DEV)   # [0] = rescale count, [8:] = timeline words
     lib.a3d_debug_set_attn_trace(C.c_void_p(counter.data_ptr()))
     try:
         ops.attention(vq, vk, vv, out, (cdim, lq * cdim, lq * cdim, lq * cdim), heads=HEADS, d=d, scale=scale, impl=L.IMPL_TC)

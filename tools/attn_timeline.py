@@ -12,15 +12,16 @@ from animate3d_b200 import _lib as L
 from tools import kernel_bench as kb
 
 lib = L.load()
-flags = int(sys.argv[1]) if len(sys.argv) > 1 else 3        # bit 0: early barrier tests, bit 1: TS-mode P V
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 15       # bit 0: early barrier tests, bit 1: TS-mode P V, bit 2: one tile per CTA, bit 3: late P-buffer check
 early = flags
 L.check(lib.a3d_debug_set_attn_poly(flags))
-buf = torch.zeros(8 + 4 * 32 * 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(8 + 4 * 32 * 8 + 32, dtype=torch.int64, device="cuda")
 kb.attn_case("warm", 2, 4, 16, 1024, 40)
 lib.a3d_debug_set_attn_trace(C.c_void_p(buf.data_ptr()))
 kb.attn_case(f"l0 cross-view flags={early} (traced)", 2, 4, 16, 1024, 40)
 lib.a3d_debug_set_attn_trace(C.c_void_p(None))
-t = buf[8:].cpu().view(4, 32, 8)
+t = buf[8:8 + 4 * 32 * 8].cpu().view(4, 32, 8)
+cta = buf[8 + 4 * 32 * 8:].cpu().view(4, 8)
 t0 = int(t[:, 0, 0].min())
 names = ["top", "s_in_regs", "p_free", "exp_done", "published"]
 print("warp = (tile g, key half h); columns: cycles since the first warp's step 0")
@@ -36,4 +37,8 @@ ph = {"wait+ldtm": (0, 1), "p_free": (1, 2), "exp": (2, 3), "publish": (3, 4)}
 for k, (a, b) in ph.items():
     v = (t[:, 8:32, b] - t[:, 8:32, a]).float()
     print(f"{k:14s} mean {v.mean():7.0f}  min {v.min():7.0f}  max {v.max():7.0f}")
-L.check(lib.a3d_debug_set_attn_poly(3))
+print("CTA life cycles (cycles since entry): set-up done | first scores in registers | step loop done | accumulators complete | rows stored | exit")
+for k in range(4):
+    c = [int(x) for x in cta[k]]
+    print(f"CTA at {k}/4 of the grid on SM {c[7]:3d}: " + " | ".join(f"{c[i] - c[0]:7d}" for i in range(1, 7)))
+L.check(lib.a3d_debug_set_attn_poly(15))

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python tools/attn_variants.py > gpurun_out/r2q_attn_variants.txt 2>&1
+timeout 300 python tools/attn_timeline.py 7 > gpurun_out/r2q_timeline.txt 2>&1
+timeout 900 python -m pytest tests/test_attention_adversarial_gpu.py tests/test_kernels_gpu.py tests/test_processors_gpu.py -q -m gpu --tb=short -p no:cacheprovider 2>&1 | tail -n 12 > gpurun_out/r2q_pytest.log
+timeout 300 python tools/kernel_bench.py gemm > gpurun_out/r2q_kernel_bench.txt 2>&1
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2q_bench.json 2> gpurun_out/r2q_bench.err
+cat gpurun_out/r2q_attn_variants.txt; grep "g=0" gpurun_out/r2q_timeline.txt | tail -6; tail -n 8 gpurun_out/r2q_timeline.txt;  tail -n 4 gpurun_out/r2q_pytest.log; cat gpurun_out/r2q_kernel_bench.txt; python - <<'P'
+import json
+for l in open('gpurun_out/r2q_bench.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print({k:d[k] for k in ('value','ms_per_step')}, d['roofline']['ms_per_launch'], d['roofline']['mufu'], d['clocks'])
+P
+tail -n 3 gpurun_out/r2q_bench.err

@@ -25,14 +25,14 @@ def timeit(fn, iters=10, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-def gemm_case(name, M, N, K, conv=None, geglu=False, rowbias=False, res=False):
+def gemm_case(name, M, N, K, conv=None, geglu=False, rowbias=False, res=False, rb=(16, 1024)):
     A = torch.randn(M if conv is None else conv[0] * conv[1] * conv[2], K if conv is None else conv[3], device=dev).half()
     B = (torch.randn(N, K, device=dev) * 0.05).half()
     out = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=torch.float16)
     bias = torch.randn(N, device=dev)
-    rb = torch.randn(1024, N, device=dev) if rowbias else None
+    rbt = torch.randn(1024, N, device=dev) if rowbias else None
     R2 = torch.randn(M, N, device=dev).half() if res else None
-    fn = lambda: ops.gemm(A, B, out, M=M, N=N, K=K, conv=conv, bias=bias, geglu=geglu, rowbias=rb, rb_div=16, rb_mod=1024, R2=R2)
+    fn = lambda: ops.gemm(A, B, out, M=M, N=N, K=K, conv=conv, bias=bias, geglu=geglu, rowbias=rbt, rb_div=rb[0], rb_mod=rb[1], R2=R2)
     ms = timeit(fn)
     fl = 2.0 * M * N * K
     ob = out.numel() * 2
@@ -72,8 +72,8 @@ if __name__ == "__main__":
         gemm_case("l0 proj 320->320", M0, 320, 320)
         gemm_case("l0 proj+res 320->320", M0, 320, 320, res=True)
         gemm_case("l0 qkv 320->1536", M0, 1536, 320)
-        gemm_case("l0 tqkv+rowbias 320->960", M0, 960, 320, rowbias=True)
-        gemm_case("l0 sqkv+rowbias 320->1152", M0, 1152, 320, rowbias=True)
+        gemm_case("l0 tqkv+rowbias(16 rows) 960", M0, 960, 320, rowbias=True, rb=(1, 16))
+        gemm_case("l0 sqkv+rowbias(8 rows) 1152", M0, 1152, 320, rowbias=True)
         gemm_case("l0 geglu 320->2560", M0, 2560, 320, geglu=True)
         gemm_case("l0 ffout 1280->320", M0, 320, 1280, res=True)
         gemm_case("l1 conv3x3 640->640", M0 // 4, 640, 5760, conv=(128, 16, 16, 640, 1))
