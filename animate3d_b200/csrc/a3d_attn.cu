@@ -31,7 +31,7 @@ struct AttnDev {
   int accumulate;
   float out_scale;
   int early_test;            // head-dim-40 kernel: non-blocking barrier tests one step ahead (see the step loop)
-  int late_pfree;            // head-dim-40 kernel, TS: test "P buffer consumed" after the exponentials instead of before them
+  int late_pfree;            // head-dim-40 kernel, TS: no explicit "P buffer consumed" wait (implied by s_full, see the step loop)
   unsigned long long* dbg;   // debug (null in production): dbg[0] counts (warp, step) pairs that took the lazy-rescale branch;
                              // dbg[8 + (w*32 + j)*8 + k]: clock64 timeline of 4 softmax warps of CTA (0,0,0) (head-dim-40 kernel)
 };
@@ -1023,7 +1023,9 @@ attn5_tc_kernel(const AttnDev p, const __grid_constant__ CUtensorMap mapQ, const
             if (!TS) st_shared_v4(sPg + p_off[c16], q);
           }
           if (TS) {
-            if (late && j >= 2 && pass == 0 && !mbar_test(&my_pv_done[j & 1], ((j - 2) >> 1) & 1)) mbar_wait(&my_pv_done[j & 1], ((j - 2) >> 1) & 1);
+            // "P buffer of step j-2 consumed" needs no barrier of its own here: the MMA warp issued P V(j-2) BEFORE Q K^T(j), tcgen05
+            // operations of one thread complete in order and tcgen05.commit tracks all of its earlier ones, so having seen
+            // s_full(j) at the top of this step already implies P V(j-2) has retired (late_pfree = 0 keeps the explicit wait)
             tmem_st16(tmem_base + lane_addr + Cfg::kColP + (uint32_t)(b * 32 + h * 16), pk);
           }
           if (pass > 0 || j == 0) break;

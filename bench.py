@@ -190,11 +190,12 @@ def run_reference(args, rank, world):
 
 
 def mufu_note(att_flops, att_ms, clocks):
-    """The pipe that actually bounds this kernel at head_dim 40: one ex2 per score at 8 cycles per
-    warp instruction per SM sub-partition plus one F2FP per score pair at 4 (profiles/r01_pipes_ubench.txt)."""
+    """The pipe that bounds this kernel at head_dim 40: one ex2 per score, MUFU.EX2 = 8 cycles per warp
+    instruction per SM sub-partition.  The fp16 pack (F2FP, 4 cycles) runs beside it, not on it: 2 MUFU + 1 F2FP measure 16.0
+    cycles, not 20 (profiles/r02_pipes_ubench.txt; round 1 had assumed a shared pipe and a 25 % higher floor)."""
     try:
         scores = att_flops / (4.0 * 40.0)                       # 4 * d FLOP per (query, key) pair
-        cycles = (scores / 32.0 * 8.0 + scores / 64.0 * 4.0) / (148 * 4)
+        cycles = (scores / 32.0 * 8.0) / (148 * 4)
         mhz = float(clocks.get("sm_mhz") or 1965.0)
         floor_ms = cycles / (mhz * 1e3)
         return {"floor_ms": floor_ms, "frac_of_floor": floor_ms / att_ms, "sm_mhz_used": mhz}
@@ -640,7 +641,7 @@ def run_native(args, rank, world, local_rank):
                      "ms_per_launch": att_ms, "flop_per_launch": att_flops, "peak_source": peak_src,
                      "mufu": mufu_note(att_flops, att_ms, clocks),
                      "note": "0.6x of the tensor peak is not reachable at head_dim 40: every score needs one exponential; the XU "
-                             "pipe (MUFU.EX2 8 cycles / warp instruction + F2FP 4) floors the kernel at `mufu.floor_ms` "
+                             "pipe (MUFU.EX2, 8 cycles / warp instruction / sub-partition) floors the kernel at `mufu.floor_ms` "
                              "(tensor-only bound would be 0.31 ms); logits here are randn, the in-step kernel time agrees within 2 %"},
         "roofline_gemm": gemm_rf,
         "splat": splat,

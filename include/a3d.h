@@ -279,8 +279,8 @@ int a3d_arap(const float* nodes, int Nt, int Nv, const int32_t* nbr, int K, cons
    head-dim-40 kernel (tools/attn_timeline.py) */
 int a3d_debug_set_attn_trace(void* device_counter_u64);
 /* tuning hook of the head-dim-40 attention kernel (default 15 = all on): bit 0 one-step-ahead non-blocking barrier tests, bit 1
-   probabilities through tensor memory (TS-mode P V), bit 2 one 128-query tile per CTA with two CTAs per SM, bit 3 (TS) "P buffer
-   consumed" checked after the exponentials instead of before them */
+   probabilities through tensor memory (TS-mode P V), bit 2 one 128-query tile per CTA with two CTAs per SM, bit 3 (TS) no explicit
+   "P buffer consumed" wait (implied by the arrival of the step's scores: tcgen05 operations retire in issue order) */
 int a3d_debug_set_attn_poly(int flags);
 /* measurement hooks of the rasterizer (bench.py's splat roofline): with timing enabled every forward / backward records CUDA
    events at its stage boundaries; a3d_debug_raster_stage_ms returns the milliseconds of the last forward's stages

@@ -12,7 +12,7 @@ from animate3d_b200 import _lib as L
 from tools import kernel_bench as kb
 
 lib = L.load()
-flags = int(sys.argv[1]) if len(sys.argv) > 1 else 15       # bit 0: early barrier tests, bit 1: TS-mode P V, bit 2: one tile per CTA, bit 3: late P-buffer check
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 15       # bit 0: early barrier tests, bit 1: TS-mode P V, bit 2: one tile per CTA, bit 3: no explicit P-buffer wait
 early = flags
 L.check(lib.a3d_debug_set_attn_poly(flags))
 buf = torch.zeros(8 + 4 * 32 * 8 + 32, dtype=torch.int64, device="cuda")

@@ -6,10 +6,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-enum Op { EX2H2, TANHH2, MUFU, F2FP, FFMA, FFMA2, FMNMX3, LEA, MUFU_FFMA, MUFU_F2FP, MUFU2_F2FP_FFMA2, POLY, MIX50, MIX25, NOPS };
+enum Op { EX2H2, TANHH2, MUFU, F2FP, FFMA, FFMA2, FMNMX3, LEA, MUFU_FFMA, MUFU_F2FP, MUFU2_F2FP_FFMA2, POLY, MIX50, MIX25, CH_MUFU2_F2FP, CH_SOFTMAX, CH_SOFTMAX_NOMAX, NOPS };
 static const char* kNames[] = {"ex2.approx.ftz.f16x2", "tanh.approx.f16x2", "MUFU.EX2", "F2FP.F16.F32.PACK", "FFMA", "FFMA2", "FMNMX3", "LEA/IADD", "MUFU+FFMA 1:1",
                                "MUFU+F2FP 2:1", "softmax pair: FFMA2+2MUFU+F2FP+FMNMX3", "poly pair (13 ops)",
-                               "mix: 1 mufu pair + 1 poly pair", "mix: 3 mufu pairs + 1 poly pair"};
+                               "mix: 1 mufu pair + 1 poly pair", "mix: 3 mufu pairs + 1 poly pair",
+                               "chained: 2 MUFU + 1 F2FP (same pipe -> 20 cycles, separate -> 16)", "chained softmax pair: FFMA2 + 2 MUFU + F2FP + FMNMX3",
+                               "chained softmax pair without FMNMX3"};
 
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t ex2h2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
@@ -84,8 +86,24 @@ __global__ void __launch_bounds__(1024, 1) bench(float* out, long long* cycles, 
       if (OP == POLY) acc ^= pair_poly(xx[u], c2, m2, mx);
       if (OP == MIX50) acc ^= (u & 1) ? pair_poly(xx[u], c2, m2, mx) : pair_mufu(xx[u], c2, m2, mx);
       if (OP == MIX25) acc ^= ((u & 3) == 3) ? pair_poly(xx[u], c2, m2, mx) : pair_mufu(xx[u], c2, m2, mx);
+      // loop-carried versions (round 1's MUFU_F2FP / "softmax pair" lines had loop-invariant inputs and were folded by the compiler)
+      if (OP == CH_MUFU2_F2FP) {
+        float a, b;
+        upk(xx[u], a, b);
+        a = ex2(a); b = ex2(b);
+        xx[u] = pk(a, b);                      // two MUFU chains per unit
+        acc ^= f2fp(a, b);                     // one conversion of their results
+      }
+      if (OP == CH_SOFTMAX || OP == CH_SOFTMAX_NOMAX) {
+        float a, b, sa, sb;
+        upk(xx[u], sa, sb);
+        if (OP == CH_SOFTMAX) mx = fmax3(mx, sa, sb);
+        xx[u] = ffma2(xx[u], c2, m2);          // the scores keep changing: nothing is loop-invariant
+        upk(xx[u], a, b);
+        acc ^= f2fp(ex2(a), ex2(b));
+      }
     }
-    if (OP >= MUFU2_F2FP_FFMA2) {   // keep the inputs changing without adding work per pair
+    if (OP >= MUFU2_F2FP_FFMA2 && OP < CH_MUFU2_F2FP) {   // keep the inputs changing without adding work per pair
       xx[it & (U - 1)] = pk(mx, __uint_as_float(acc));
     }
   }
@@ -131,6 +149,9 @@ int main() {
     run<POLY>(w, out, cyc, 13);
     run<MIX50>(w, out, cyc, 9);
     run<MIX25>(w, out, cyc, 7);
+    run<CH_MUFU2_F2FP>(w, out, cyc, 3);
+    run<CH_SOFTMAX>(w, out, cyc, 5);
+    run<CH_SOFTMAX_NOMAX>(w, out, cyc, 4);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
