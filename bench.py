@@ -636,8 +636,8 @@ def run_native(args, rank, world, local_rank):
                    "cuda_graph": bool(model.use_cuda_graph)},
         "roofline": {"bound": "tensor", "kernel": "a3d_attention head_dim 40 (fused cross-view attention, L=4096, 32 batches x 8 heads)",
                      "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf, "traffic": traffic,
-                     "traffic_source": "ncu --set full dram__bytes_read+write of this kernel, round-1 capture (profiles/roofline_traffic.json, "
-                                       "profiles/r01_ncu_attn5.txt); algorithmic bytes 403 MB",
+                     "traffic_source": "ncu --set full dram__bytes_read+write of this kernel, round-2 capture (profiles/roofline_traffic.json, "
+                                       "profiles/r02_ncu_attn5.txt); algorithmic bytes 386 MB",
                      "ms_per_launch": att_ms, "flop_per_launch": att_flops, "peak_source": peak_src,
                      "mufu": mufu_note(att_flops, att_ms, clocks),
                      "note": "0.6x of the tensor peak is not reachable at head_dim 40: every score needs one exponential; the XU "
