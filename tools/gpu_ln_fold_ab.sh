@@ -1,4 +1,5 @@
 #!/bin/bash
+# A/B of the LayerNorm-into-GEMM fold: meaningful only with profiles/r02_ln_fold_experiment.patch applied (A3D_FUSE_LN is read by that patch).
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu --tb=short -p no:cacheprovider -k "gemm or layer_norm" 2>&1 | tail -n 15 > gpurun_out/r2x1_pytest.log
 A3D_FUSE_LN=0 timeout 300 python tools/op_breakdown.py > gpurun_out/r2x1_breakdown_unfused.txt 2>&1
